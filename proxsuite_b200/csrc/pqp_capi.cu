@@ -1,0 +1,954 @@
+// Host side of the C-ABI (include/pqp.h): device memory management, the
+// init / update / warm-start / solve state machine of the reference's QP<T>
+// object applied to a whole batch, shared-memory layout policy and launches.
+//
+// Reference semantics followed here (relative to
+// /root/reference/include/proxsuite/proxqp):
+//   dense/wrapper.hpp:354-498, 520-703   QP::init
+//   dense/wrapper.hpp:723-918            QP::update
+//   dense/wrapper.hpp:922-962            QP::solve / cleanup
+//   dense/helpers.hpp:176-189, 502-572, 680-763   setup / proximal parameters / warm_start
+//   dense/solver.hpp:1125-1377           qp_solve prologue (dirty / initial guess matrix)
+//   results.hpp:149-203                  Results::cleanup / cold_start / cleanup_statistics
+//   dense/workspace.hpp:330-377          Workspace::cleanup (flags)
+// There is no CPU fallback anywhere in this file: without a usable CUDA
+// device every entry point that computes returns PQP_ECUDA.
+#include "pqp_device.h"
+#include "random_qp.hpp"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int
+fail(int code, const std::string& msg)
+{
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                                                                                                                                                                         \
+  do {                                                                                                                                                                                                                                                         \
+    cudaError_t e__ = (expr);                                                                                                                                                                                                                                  \
+    if (e__ != cudaSuccess) return fail(PQP_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                                                                                                                                                     \
+  } while (0)
+
+struct QpFlags
+{
+  bool dirty = false, refactorize = false, proximal_parameter_update = false, is_initialized = false;
+};
+
+} // namespace
+
+struct pqp_batch
+{
+  int64_t B = 0;
+  PqpDims d{};
+  int backend = PQP_BACKEND_PRIMAL_DUAL_LDLT;
+  int device = 0;
+  PqpBatchPtrs p{};
+  std::vector<void*> allocs;
+  std::vector<PqpQpParams> hparams; // settings (host truth) + launch parameters
+  std::vector<pqp_info> hinfo;      // results.info (host truth between solves)
+  std::vector<QpFlags> flags;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  bool setup_timed = false, solve_timed = false;
+  PqpLayout lay{};
+  int grid = 0;
+  int32_t* counter = nullptr;
+  double* ws = nullptr;
+  double* dbg = nullptr;
+  int dbg_cap = 0;
+  int64_t launches = 0;
+  bool solve_pending = false;
+};
+
+namespace {
+
+template<class T>
+int
+dev_alloc(pqp_batch* b, T** out, size_t count)
+{
+  void* ptr = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&ptr, bytes);
+  if (e != cudaSuccess) return fail(PQP_ECUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  cudaMemset(ptr, 0, bytes);
+  b->allocs.push_back(ptr);
+  *out = static_cast<T*>(ptr);
+  return 0;
+}
+
+void
+info_defaults(pqp_info& i, const pqp_settings* s, int backend)
+{
+  // results.hpp:90-143 (ctor) + cold_start(settings) :175-194
+  i.rho = (backend == PQP_BACKEND_PRIMAL_LDLT) ? 1e-5 : 1e-6;
+  i.mu_eq = 1e-3;
+  i.mu_eq_inv = 1e3;
+  i.mu_in = 1e-1;
+  i.mu_in_inv = 1e1;
+  i.nu = 1.0;
+  i.minimal_H_eigenvalue_estimate = 0;
+  if (s) {
+    i.rho = s->default_rho;
+    i.mu_eq = s->default_mu_eq;
+    i.mu_eq_inv = 1.0 / i.mu_eq;
+    i.mu_in = s->default_mu_in;
+    i.mu_in_inv = 1.0 / i.mu_in;
+    i.minimal_H_eigenvalue_estimate = s->default_H_eigenvalue_estimate;
+  }
+}
+void
+cleanup_statistics(pqp_info& i)
+{
+  // results.hpp:157-174
+  i.run_time = i.setup_time = i.solve_time = 0;
+  i.objValue = 0;
+  i.iter = i.iter_ext = i.mu_updates = i.rho_updates = 0;
+  i.pri_res = i.dua_res = i.duality_gap = i.iterative_residual = 0;
+  i.status = PQP_MAX_ITER_REACHED;
+}
+void
+cold_start(pqp_info& i, const pqp_settings* s, int backend)
+{
+  info_defaults(i, s, backend);
+  cleanup_statistics(i);
+}
+
+// Shared-memory placement policy. Everything that does not fit the budget
+// lives in the per-CTA global workspace (L2-resident).
+int
+make_layout(pqp_batch* b)
+{
+  const PqpDims& d = b->d;
+  PqpLayout& L = b->lay;
+  std::memset(&L, 0, sizeof(L));
+  const int n = d.n, ne = d.ne, nc = d.nc, cap = d.cap;
+  auto rnd = [](int64_t v) { return (v + 1) & ~int64_t(1); };
+  // vector arena
+  int vsz[V_COUNT];
+  for (int& v : vsz) v = 0;
+  vsz[V_X] = n; vsz[V_Y] = ne; vsz[V_Z] = nc; vsz[V_XP] = n; vsz[V_YP] = ne; vsz[V_ZP] = nc;
+  vsz[V_DX] = n; vsz[V_DS] = cap; vsz[V_DZ] = nc;
+  vsz[V_RX] = n; vsz[V_RS] = cap; vsz[V_EX] = n; vsz[V_ES] = cap;
+  vsz[V_DUAL] = n; vsz[V_SE] = ne; vsz[V_RUP] = nc; vsz[V_SI] = nc;
+  vsz[V_HDX] = n; vsz[V_ADX] = ne; vsz[V_ATDY] = n; vsz[V_CDX] = nc; vsz[V_CTDZ] = n; vsz[V_Q] = n;
+  vsz[V_GS] = n; vsz[V_BS] = ne; vsz[V_US] = nc; vsz[V_LS] = nc; vsz[V_IS] = n; vsz[V_DELTA] = n + ne + nc;
+  vsz[V_B] = ne; vsz[V_U] = nc; vsz[V_L] = nc;
+  vsz[V_D1INV] = n; vsz[V_DSV] = cap; vsz[V_DSINV] = cap;
+  vsz[V_T1] = n; vsz[V_T2] = n; vsz[V_T3] = n;
+  vsz[V_S1] = cap + 1; vsz[V_S2] = cap + 1; vsz[V_S3] = cap + 1; vsz[V_S4] = cap + 1;
+  vsz[V_ALPHAS] = 2 * nc + 2; vsz[V_GRADS] = 4;
+  vsz[V_SCRATCH] = PQP_NT; vsz[V_RED] = 128;
+  int off = 0;
+  for (int v = 0; v < V_COUNT; ++v) {
+    L.voff[v] = off;
+    off += (int)rnd(vsz[v]);
+  }
+  L.vec_doubles = off;
+  L.scratch_doubles = PQP_NT;
+  int64_t sz[PA_COUNT];
+  sz[PA_M1] = (d.hess == PQP_HESSIAN_DENSE) ? rnd((int64_t)n * (n - 1) / 2) : 2;
+  sz[PA_AS] = rnd((int64_t)ne * n);
+  sz[PA_MS] = rnd((int64_t)cap * (cap - 1) / 2 + 2);
+  sz[PA_G] = rnd((int64_t)cap * (cap + 1) / 2 + 2);
+  sz[PA_Y] = 2;
+  sz[PA_VEC] = L.vec_doubles;
+  const int64_t nlist = std::max(nc, cap);
+  L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);
+  int max_smem = pqp_solve_max_smem();
+  if (max_smem <= 0) return fail(PQP_ECUDA, "no CUDA device / cannot query shared memory");
+  int64_t budget = (int64_t)max_smem - 1024 /*static*/ - L.smem_int_bytes;
+  if (const char* e = std::getenv("PQP_SMEM_BUDGET")) {
+    int64_t v = std::atoll(e);
+    if (v > 0) budget = std::min(budget, v - 1024 - (int64_t)L.smem_int_bytes);
+  }
+  int64_t smem_d = 0, ws_d = 0;
+  auto put = [&](int id, bool want_smem) {
+    if (want_smem && (smem_d + sz[id]) * 8 <= budget) {
+      L.in_smem[id] = 1;
+      L.off[id] = smem_d;
+      smem_d += sz[id];
+    } else {
+      L.in_smem[id] = 0;
+      L.off[id] = ws_d;
+      ws_d += sz[id];
+    }
+  };
+  put(PA_VEC, true);
+  put(PA_M1, true);
+  put(PA_MS, true);
+  put(PA_AS, true);
+  put(PA_G, false);
+  put(PA_Y, false);
+  L.smem_doubles = (int32_t)smem_d;
+  L.ws_doubles = std::max<int64_t>(ws_d, 2);
+  return 0;
+}
+
+int
+check_range(pqp_batch* b, int64_t first, int64_t count)
+{
+  if (!b) return fail(PQP_EINVAL, "null batch");
+  if (first < 0 || count < 0 || first + count > b->B) return fail(PQP_EINVAL, "wrong argument size: QP index range out of bounds");
+  return 0;
+}
+
+int
+copy_in(pqp_batch* b, double* dst_base, const double* src, int64_t first, int64_t count, int64_t per_qp, bool src_is_device)
+{
+  if (!src || per_qp == 0 || count == 0) return 0;
+  CUDA_TRY(cudaMemcpyAsync(dst_base + first * per_qp, src, sizeof(double) * (size_t)(count * per_qp), src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, b->stream));
+  return 0;
+}
+
+// helpers.hpp:680-705
+void
+update_proximal_parameters(pqp_batch* b, int64_t i, const double* rho, const double* mu_eq, const double* mu_in)
+{
+  pqp_settings& s = b->hparams[i].s;
+  pqp_info& info = b->hinfo[i];
+  QpFlags& f = b->flags[i];
+  if (rho) {
+    s.default_rho = *rho;
+    info.rho = *rho;
+    f.proximal_parameter_update = true;
+  }
+  if (mu_eq) {
+    s.default_mu_eq = *mu_eq;
+    info.mu_eq = *mu_eq;
+    info.mu_eq_inv = 1.0 / info.mu_eq;
+    f.proximal_parameter_update = true;
+  }
+  if (mu_in) {
+    s.default_mu_in = *mu_in;
+    info.mu_in = *mu_in;
+    info.mu_in_inv = 1.0 / info.mu_in;
+    f.proximal_parameter_update = true;
+  }
+}
+// helpers.hpp:176-189
+void
+update_default_rho(pqp_batch* b, int64_t i, const double* manual)
+{
+  pqp_settings& s = b->hparams[i].s;
+  pqp_info& info = b->hinfo[i];
+  if (manual) {
+    s.default_H_eigenvalue_estimate = *manual;
+    info.minimal_H_eigenvalue_estimate = s.default_H_eigenvalue_estimate;
+  }
+  s.default_rho += std::fabs(info.minimal_H_eigenvalue_estimate);
+  info.rho = s.default_rho;
+}
+
+int
+zero_results(pqp_batch* b, int64_t i)
+{
+  const PqpDims& d = b->d;
+  CUDA_TRY(cudaMemsetAsync(b->p.x + i * d.n, 0, sizeof(double) * d.n, b->stream));
+  if (d.ne) CUDA_TRY(cudaMemsetAsync(b->p.y + i * d.ne, 0, sizeof(double) * d.ne, b->stream));
+  if (d.ne) CUDA_TRY(cudaMemsetAsync(b->p.se + i * d.ne, 0, sizeof(double) * d.ne, b->stream));
+  if (d.nc) CUDA_TRY(cudaMemsetAsync(b->p.z + i * d.nc, 0, sizeof(double) * d.nc, b->stream));
+  if (d.nc) CUDA_TRY(cudaMemsetAsync(b->p.si + i * d.nc, 0, sizeof(double) * d.nc, b->stream));
+  return 0;
+}
+
+// helpers.hpp:522-572: what setup() does to results / workspace flags
+int
+setup_results_and_flags(pqp_batch* b, int64_t i)
+{
+  pqp_settings& s = b->hparams[i].s;
+  pqp_info& info = b->hinfo[i];
+  QpFlags& f = b->flags[i];
+  auto work_cleanup = [&]() { f = QpFlags(); };
+  switch (s.initial_guess) {
+    case PQP_EQUALITY_CONSTRAINED_INITIAL_GUESS:
+    case PQP_NO_INITIAL_GUESS:
+    case PQP_WARM_START: {
+      bool ppu = f.proximal_parameter_update;
+      if (int rc = zero_results(b, i)) return rc;
+      if (ppu)
+        cleanup_statistics(info);
+      else
+        cold_start(info, &s, b->backend);
+      work_cleanup();
+    } break;
+    case PQP_COLD_START_WITH_PREVIOUS_RESULT: {
+      if (f.proximal_parameter_update)
+        cleanup_statistics(info);
+      else
+        cold_start(info, &s, b->backend);
+      work_cleanup();
+    } break;
+    case PQP_WARM_START_WITH_PREVIOUS_RESULT: {
+      if (f.refactorize || f.proximal_parameter_update) {
+        work_cleanup();
+        f.refactorize = true;
+      }
+      cleanup_statistics(info);
+    } break;
+    default:
+      return fail(PQP_EINVAL, "invalid initial_guess");
+  }
+  return 0;
+}
+
+int
+launch_setup(pqp_batch* b, int64_t first, int64_t count, bool execute, bool reset_scaling)
+{
+  // device needs the settings (preconditioner parameters) of these QPs
+  CUDA_TRY(cudaMemcpyAsync(b->p.params + first, b->hparams.data() + first, sizeof(PqpQpParams) * (size_t)count, cudaMemcpyHostToDevice, b->stream));
+  PqpSetupArgs a{};
+  a.d = b->d;
+  a.p = b->p;
+  a.first = (int32_t)first;
+  a.count = (int32_t)count;
+  a.execute = execute ? 1 : 0;
+  a.reset_scaling = reset_scaling ? 1 : 0;
+  CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+  int rc = pqp_launch_setup(&a, b->stream);
+  if (rc != 0) return fail(PQP_ECUDA, std::string("setup kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+  CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+  b->setup_timed = true;
+  b->launches += 1;
+  return 0;
+}
+
+int
+do_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const double* g, const double* A, const double* b_, const double* C, const double* l, const double* u, const double* l_box, const double* u_box, int compute_preconditioner,
+        const double* rho, const double* mu_eq, const double* mu_in, const double* manual_eig, bool dev_ptrs)
+{
+  if (int rc = check_range(b, first, count)) return rc;
+  const PqpDims& d = b->d;
+  if (!d.box && (l_box || u_box))
+    return fail(PQP_EINVAL, "wrong model setup: the QP object is designed without box constraints, but is initialized with lower or upper box inequalities.");
+  CUDA_TRY(cudaSetDevice(b->device));
+  for (int64_t i = first; i < first + count; ++i) {
+    pqp_settings& s = b->hparams[i].s;
+    QpFlags& f = b->flags[i];
+    s.compute_preconditioner = compute_preconditioner ? 1 : 0;
+    f.refactorize = (s.initial_guess == PQP_WARM_START_WITH_PREVIOUS_RESULT); // wrapper.hpp:452-459
+    f.proximal_parameter_update = false;
+    update_proximal_parameters(b, i, rho, mu_eq, mu_in);
+    update_default_rho(b, i, manual_eig);
+    if (int rc = setup_results_and_flags(b, i)) return rc;
+    f.is_initialized = true;
+  }
+  const int64_t n = d.n, ne = d.ne, ni = d.ni;
+  if (int rc = copy_in(b, b->p.H, H, first, count, n * n, dev_ptrs)) return rc;
+  if (int rc = copy_in(b, b->p.g, g, first, count, n, dev_ptrs)) return rc;
+  if (int rc = copy_in(b, b->p.A, A, first, count, ne * n, dev_ptrs)) return rc;
+  if (int rc = copy_in(b, b->p.b, b_, first, count, ne, dev_ptrs)) return rc;
+  if (int rc = copy_in(b, b->p.C, C, first, count, ni * n, dev_ptrs)) return rc;
+  if (int rc = copy_in(b, b->p.l, l, first, count, ni, dev_ptrs)) return rc;
+  if (int rc = copy_in(b, b->p.u, u, first, count, ni, dev_ptrs)) return rc;
+  if (d.box) {
+    if (int rc = copy_in(b, b->p.l_box, l_box, first, count, n, dev_ptrs)) return rc;
+    if (int rc = copy_in(b, b->p.u_box, u_box, first, count, n, dev_ptrs)) return rc;
+  }
+  return launch_setup(b, first, count, compute_preconditioner != 0, compute_preconditioner == 0);
+}
+
+void
+fill_vec(std::vector<double>& v, double val)
+{
+  std::fill(v.begin(), v.end(), val);
+}
+
+} // namespace
+
+extern "C" {
+
+const char*
+pqp_last_error(void)
+{
+  return g_err.c_str();
+}
+const char*
+pqp_version(void)
+{
+  return "proxsuite_b200 0.1.0 (sm_100a)";
+}
+
+void
+pqp_settings_default(pqp_settings* s, int dense_backend)
+{
+  // settings.hpp:213-315
+  std::memset(s, 0, sizeof(*s));
+  s->default_rho = (dense_backend == PQP_BACKEND_PRIMAL_LDLT) ? 1e-5 : 1e-6;
+  s->default_mu_eq = 1e-3;
+  s->default_mu_in = 1e-1;
+  s->alpha_bcl = 0.1;
+  s->beta_bcl = 0.9;
+  s->refactor_dual_feasibility_threshold = 1e-2;
+  s->refactor_rho_threshold = 1e-7;
+  s->mu_min_eq = 1e-9;
+  s->mu_min_in = 1e-8;
+  s->mu_max_eq_inv = 1e9;
+  s->mu_max_in_inv = 1e8;
+  s->mu_update_factor = 0.1;
+  s->mu_update_inv_factor = 10;
+  s->cold_reset_mu_eq = 1. / 1.1;
+  s->cold_reset_mu_in = 1. / 1.1;
+  s->cold_reset_mu_eq_inv = 1.1;
+  s->cold_reset_mu_in_inv = 1.1;
+  s->eps_abs = 1e-5;
+  s->eps_rel = 0;
+  s->eps_refact = 1e-6;
+  s->eps_duality_gap_abs = 1e-4;
+  s->eps_duality_gap_rel = 0;
+  s->preconditioner_accuracy = 1e-3;
+  s->eps_primal_inf = 1e-4;
+  s->eps_dual_inf = 1e-4;
+  s->alpha_gpdal = 0.95;
+  s->default_H_eigenvalue_estimate = 0;
+  s->max_iter = 10000;
+  s->max_iter_in = 1500;
+  s->safe_guard = 10000;
+  s->nb_iterative_refinement = 10;
+  s->preconditioner_max_iter = 10;
+  s->frequence_infeasibility_check = 1;
+  s->verbose = 0;
+  s->initial_guess = PQP_EQUALITY_CONSTRAINED_INITIAL_GUESS;
+  s->update_preconditioner = 0;
+  s->compute_preconditioner = 1;
+  s->compute_timings = 0;
+  s->check_duality_gap = 0;
+  s->bcl_update = 1;
+  s->merit_function_type = PQP_MERIT_GPDAL;
+  s->primal_infeasibility_solving = 0;
+}
+
+int
+pqp_dense_backend_choice(int backend, int64_t dim, int64_t n_eq, int64_t n_in, int box)
+{
+  // wrapper.hpp:82-113
+  if (backend != PQP_BACKEND_AUTOMATIC) return backend;
+  int64_t ncons = n_in + (box ? dim : 0);
+  double d = double(dim);
+  double pd = 0.5 * std::pow(double(n_eq) / d, 2) + 0.17 * (std::pow(double(n_eq) / d, 3) + std::pow(double(ncons) / d, 3)) + 0.2 * std::pow(double(n_eq + ncons) / d, 2) / d;
+  double pl = 1.5 * ((0.5 * double(n_eq) + double(ncons)) / d + 0.2 / d);
+  return pd > pl ? PQP_BACKEND_PRIMAL_LDLT : PQP_BACKEND_PRIMAL_DUAL_LDLT;
+}
+
+pqp_batch*
+pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box, int hessian, int backend, int device)
+{
+  if (dim <= 0) {
+    fail(PQP_EINVAL, "wrong argument size: the dimension wrt the primal variable x should be strictly positive.");
+    return nullptr;
+  }
+  if (batch < 0 || n_eq < 0 || n_in < 0 || hessian < 0 || hessian > 2) {
+    fail(PQP_EINVAL, "wrong argument: negative size or invalid hessian type");
+    return nullptr;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fail(PQP_ECUDA, "no CUDA device available: proxsuite_b200 has no CPU fallback");
+    return nullptr;
+  }
+  if (device < 0) cudaGetDevice(&device);
+  if (cudaSetDevice(device) != cudaSuccess) {
+    fail(PQP_ECUDA, "cudaSetDevice failed");
+    return nullptr;
+  }
+  pqp_batch* b = new pqp_batch;
+  b->B = batch;
+  b->device = device;
+  // Both dense backends are served by the same block factorisation on the
+  // device; the choice only selects default_rho.
+  b->backend = pqp_dense_backend_choice(backend, dim, n_eq, n_in, box);
+  PqpDims& d = b->d;
+  d.n = (int)dim;
+  d.ne = (int)n_eq;
+  d.ni = (int)n_in;
+  d.box = box ? 1 : 0;
+  d.nc = d.ni + (d.box ? d.n : 0);
+  d.hess = hessian;
+  d.cap = d.ne + d.nc;
+  const size_t B = (size_t)batch;
+  const size_t n = d.n, ne = d.ne, ni = d.ni, nc = d.nc;
+  int rc = 0;
+  PqpBatchPtrs& p = b->p;
+  rc |= dev_alloc(b, &p.H, B * n * n);
+  rc |= dev_alloc(b, &p.g, B * n);
+  rc |= dev_alloc(b, &p.A, B * ne * n);
+  rc |= dev_alloc(b, &p.b, B * ne);
+  rc |= dev_alloc(b, &p.C, B * ni * n);
+  rc |= dev_alloc(b, &p.l, B * ni);
+  rc |= dev_alloc(b, &p.u, B * ni);
+  rc |= dev_alloc(b, &p.l_box, B * n);
+  rc |= dev_alloc(b, &p.u_box, B * n);
+  rc |= dev_alloc(b, &p.Hs, B * n * n);
+  rc |= dev_alloc(b, &p.gs, B * n);
+  rc |= dev_alloc(b, &p.As, B * ne * n);
+  rc |= dev_alloc(b, &p.bs, B * ne);
+  rc |= dev_alloc(b, &p.Cs, B * ni * n);
+  rc |= dev_alloc(b, &p.us, B * nc);
+  rc |= dev_alloc(b, &p.ls, B * nc);
+  rc |= dev_alloc(b, &p.is, B * n);
+  rc |= dev_alloc(b, &p.delta, B * (n + ne + nc));
+  rc |= dev_alloc(b, &p.c, B);
+  rc |= dev_alloc(b, &p.x, B * n);
+  rc |= dev_alloc(b, &p.y, B * ne);
+  rc |= dev_alloc(b, &p.z, B * nc);
+  rc |= dev_alloc(b, &p.se, B * ne);
+  rc |= dev_alloc(b, &p.si, B * nc);
+  rc |= dev_alloc(b, &p.info, B * PQP_INFO_DOUBLES);
+  rc |= dev_alloc(b, &p.params, B);
+  rc |= dev_alloc(b, &b->counter, 1);
+  if (rc != 0) {
+    pqp_batch_destroy(b);
+    return nullptr;
+  }
+  // model defaults (model.hpp:70-91): u = +inf_bound, l = -inf_bound
+  {
+    const double inf_b = std::sqrt(1.7976931348623157e308);
+    std::vector<double> tmp(std::max<size_t>(B * std::max(ni, n), 1));
+    fill_vec(tmp, inf_b);
+    cudaMemcpy(p.u, tmp.data(), sizeof(double) * B * ni, cudaMemcpyHostToDevice);
+    cudaMemcpy(p.u_box, tmp.data(), sizeof(double) * B * n, cudaMemcpyHostToDevice);
+    fill_vec(tmp, -inf_b);
+    cudaMemcpy(p.l, tmp.data(), sizeof(double) * B * ni, cudaMemcpyHostToDevice);
+    cudaMemcpy(p.l_box, tmp.data(), sizeof(double) * B * n, cudaMemcpyHostToDevice);
+    std::vector<double> ones(std::max<size_t>(B * (n + ne + nc), 1), 1.0);
+    cudaMemcpy(p.delta, ones.data(), sizeof(double) * B * (n + ne + nc), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.c, ones.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
+    cudaMemcpy(p.is, ones.data(), sizeof(double) * B * n, cudaMemcpyHostToDevice);
+  }
+  b->hparams.resize(B);
+  b->hinfo.resize(B);
+  b->flags.resize(B);
+  for (size_t i = 0; i < B; ++i) {
+    std::memset(&b->hparams[i], 0, sizeof(PqpQpParams));
+    pqp_settings_default(&b->hparams[i].s, b->backend);
+    std::memset(&b->hinfo[i], 0, sizeof(pqp_info));
+    info_defaults(b->hinfo[i], nullptr, b->backend);
+    b->hinfo[i].status = PQP_NOT_RUN;
+  }
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess || cudaEventCreate(&b->ev2) != cudaSuccess ||
+      cudaEventCreate(&b->ev3) != cudaSuccess) {
+    fail(PQP_ECUDA, "stream/event creation failed");
+    pqp_batch_destroy(b);
+    return nullptr;
+  }
+  if (make_layout(b) != 0) {
+    pqp_batch_destroy(b);
+    return nullptr;
+  }
+  // persistent grid: resident CTAs per SM x SM count, never more than the batch
+  {
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    size_t smem = sizeof(double) * (size_t)b->lay.smem_doubles + (size_t)b->lay.smem_int_bytes;
+    int max_smem_sm = 0;
+    cudaDeviceGetAttribute(&max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+    int per_sm = (int)std::max<size_t>(1, (size_t)max_smem_sm / (smem + 2048));
+    per_sm = std::min(per_sm, 2048 / PQP_NT);
+    if (const char* e = std::getenv("PQP_CTAS_PER_SM")) per_sm = std::max(1, std::atoi(e));
+    int64_t g = (int64_t)sms * per_sm;
+    b->grid = (int)std::max<int64_t>(1, std::min<int64_t>(g, std::max<int64_t>(batch, 1)));
+    if (dev_alloc(b, &b->ws, (size_t)b->grid * (size_t)b->lay.ws_doubles) != 0) {
+      pqp_batch_destroy(b);
+      return nullptr;
+    }
+  }
+  if (std::getenv("PQP_DEBUG_TRACE")) {
+    b->dbg_cap = 6 * 4096;
+    dev_alloc(b, &b->dbg, (size_t)b->dbg_cap);
+  }
+  return b;
+}
+
+void
+pqp_batch_destroy(pqp_batch* b)
+{
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (void* p : b->allocs) cudaFree(p);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->ev2) cudaEventDestroy(b->ev2);
+  if (b->ev3) cudaEventDestroy(b->ev3);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int64_t
+pqp_batch_size(const pqp_batch* b)
+{
+  return b ? b->B : 0;
+}
+int
+pqp_batch_dims(const pqp_batch* b, int64_t* dim, int64_t* n_eq, int64_t* n_in, int* box, int* hessian, int* backend)
+{
+  if (!b) return fail(PQP_EINVAL, "null batch");
+  if (dim) *dim = b->d.n;
+  if (n_eq) *n_eq = b->d.ne;
+  if (n_in) *n_in = b->d.ni;
+  if (box) *box = b->d.box;
+  if (hessian) *hessian = b->d.hess;
+  if (backend) *backend = b->backend;
+  return 0;
+}
+
+int
+pqp_batch_settings_get(const pqp_batch* b, int64_t index, pqp_settings* out)
+{
+  if (!b || !out || index >= b->B) return fail(PQP_EINVAL, "bad arguments");
+  *out = b->hparams[std::max<int64_t>(index, 0)].s;
+  return 0;
+}
+int
+pqp_batch_settings_set(pqp_batch* b, int64_t index, const pqp_settings* in)
+{
+  if (!b || !in || index >= b->B) return fail(PQP_EINVAL, "bad arguments");
+  if (index < 0) {
+    for (auto& p : b->hparams) p.s = *in;
+  } else {
+    b->hparams[index].s = *in;
+  }
+  return 0;
+}
+
+int
+pqp_batch_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const double* g, const double* A, const double* b_, const double* C, const double* l, const double* u, const double* l_box, const double* u_box, int compute_preconditioner,
+               const double* rho, const double* mu_eq, const double* mu_in, const double* manual_eig)
+{
+  return do_init(b, first, count, H, g, A, b_, C, l, u, l_box, u_box, compute_preconditioner, rho, mu_eq, mu_in, manual_eig, false);
+}
+int
+pqp_batch_init_device(pqp_batch* b, int64_t first, int64_t count, const double* H, const double* g, const double* A, const double* b_, const double* C, const double* l, const double* u, const double* l_box, const double* u_box,
+                      int compute_preconditioner, const double* rho, const double* mu_eq, const double* mu_in, const double* manual_eig)
+{
+  return do_init(b, first, count, H, g, A, b_, C, l, u, l_box, u_box, compute_preconditioner, rho, mu_eq, mu_in, manual_eig, true);
+}
+
+int
+pqp_batch_update(pqp_batch* b, int64_t first, int64_t count, const double* H, const double* g, const double* A, const double* b_, const double* C, const double* l, const double* u, const double* l_box, const double* u_box, int update_preconditioner,
+                 const double* rho, const double* mu_eq, const double* mu_in, const double* manual_eig)
+{
+  if (int rc = check_range(b, first, count)) return rc;
+  const PqpDims& d = b->d;
+  if (!d.box && (l_box || u_box))
+    return fail(PQP_EINVAL, "wrong model setup: the QP object is designed without box constraints, but the update includes lower or upper box inequalities.");
+  CUDA_TRY(cudaSetDevice(b->device));
+  // wrapper.hpp:743-746: update before init == init (per QP); handle the
+  // common case where the whole range is in the same state.
+  bool all_init = true, none_init = true;
+  for (int64_t i = first; i < first + count; ++i) {
+    all_init = all_init && b->flags[i].is_initialized;
+    none_init = none_init && !b->flags[i].is_initialized;
+  }
+  if (none_init && count > 0) return do_init(b, first, count, H, g, A, b_, C, l, u, l_box, u_box, update_preconditioner, rho, mu_eq, mu_in, nullptr, false);
+  if (!all_init) return fail(PQP_ESTATE, "update on a range that mixes initialised and non-initialised QPs");
+  for (int64_t i = first; i < first + count; ++i) {
+    pqp_settings& s = b->hparams[i].s;
+    QpFlags& f = b->flags[i];
+    s.update_preconditioner = update_preconditioner ? 1 : 0;
+    f.refactorize = false;
+    f.proximal_parameter_update = false;
+    if (H || A || C) f.refactorize = true; // helpers.hpp:466-468
+    update_proximal_parameters(b, i, rho, mu_eq, mu_in);
+    update_default_rho(b, i, manual_eig);
+    if (int rc = setup_results_and_flags(b, i)) return rc;
+    // Workspace::cleanup clears is_initialized (workspace.hpp:330-377); the
+    // reference only re-sets it in qp_solve. Model data stay valid, so the
+    // batch keeps the QP solvable.
+    f.is_initialized = true;
+  }
+  const int64_t n = d.n, ne = d.ne, ni = d.ni;
+  if (int rc = copy_in(b, b->p.H, H, first, count, n * n, false)) return rc;
+  if (int rc = copy_in(b, b->p.g, g, first, count, n, false)) return rc;
+  if (int rc = copy_in(b, b->p.A, A, first, count, ne * n, false)) return rc;
+  if (int rc = copy_in(b, b->p.b, b_, first, count, ne, false)) return rc;
+  if (int rc = copy_in(b, b->p.C, C, first, count, ni * n, false)) return rc;
+  if (int rc = copy_in(b, b->p.l, l, first, count, ni, false)) return rc;
+  if (int rc = copy_in(b, b->p.u, u, first, count, ni, false)) return rc;
+  if (d.box) {
+    if (int rc = copy_in(b, b->p.l_box, l_box, first, count, n, false)) return rc;
+    if (int rc = copy_in(b, b->p.u_box, u_box, first, count, n, false)) return rc;
+  }
+  // EXECUTE recomputes the scaling, KEEP re-applies the stored one
+  return launch_setup(b, first, count, update_preconditioner != 0, false);
+}
+
+int
+pqp_batch_warm_start(pqp_batch* b, int64_t first, int64_t count, const double* x, const double* y, const double* z)
+{
+  if (int rc = check_range(b, first, count)) return rc;
+  if (!x && !y && !z) return 0;
+  CUDA_TRY(cudaSetDevice(b->device));
+  for (int64_t i = first; i < first + count; ++i) b->hparams[i].s.initial_guess = PQP_WARM_START; // sticky, helpers.hpp:727
+  if (int rc = copy_in(b, b->p.x, x, first, count, b->d.n, false)) return rc;
+  if (int rc = copy_in(b, b->p.y, y, first, count, b->d.ne, false)) return rc;
+  if (int rc = copy_in(b, b->p.z, z, first, count, b->d.nc, false)) return rc;
+  return 0;
+}
+
+int
+pqp_batch_solve_async(pqp_batch* b, void* stream_)
+{
+  if (!b) return fail(PQP_EINVAL, "null batch");
+  CUDA_TRY(cudaSetDevice(b->device));
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : b->stream;
+  // qp_solve prologue (solver.hpp:1125-1377) decided per QP on the host
+  for (int64_t i = 0; i < b->B; ++i) {
+    PqpQpParams& p = b->hparams[i];
+    pqp_info& info = b->hinfo[i];
+    QpFlags& f = b->flags[i];
+    p.active = f.is_initialized ? 1 : 0;
+    if (!p.active) continue;
+    const int ig = p.s.initial_guess;
+    if (f.dirty) {
+      switch (ig) {
+        case PQP_EQUALITY_CONSTRAINED_INITIAL_GUESS:
+        case PQP_NO_INITIAL_GUESS:
+          cold_start(info, &p.s, b->backend); // results.cleanup(settings)
+          p.start_mode = (ig == PQP_NO_INITIAL_GUESS) ? PQP_START_COLD : PQP_START_EQ_GUESS;
+          break;
+        case PQP_COLD_START_WITH_PREVIOUS_RESULT:
+        case PQP_WARM_START:
+          cold_start(info, &p.s, b->backend);
+          p.start_mode = PQP_START_WARM;
+          break;
+        default:
+          cleanup_statistics(info);
+          p.start_mode = PQP_START_WARM_KEEP;
+          break;
+      }
+    } else {
+      switch (ig) {
+        case PQP_EQUALITY_CONSTRAINED_INITIAL_GUESS: p.start_mode = PQP_START_EQ_GUESS; break;
+        case PQP_NO_INITIAL_GUESS: p.start_mode = PQP_START_COLD; break;
+        case PQP_COLD_START_WITH_PREVIOUS_RESULT:
+        case PQP_WARM_START: p.start_mode = PQP_START_WARM; break;
+        default: p.start_mode = PQP_START_WARM_KEEP; break;
+      }
+    }
+    p.rho = info.rho;
+    p.mu_eq = info.mu_eq;
+    p.mu_in = info.mu_in;
+  }
+  CUDA_TRY(cudaMemcpyAsync(b->p.params, b->hparams.data(), sizeof(PqpQpParams) * (size_t)b->B, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(b->counter, 0, sizeof(int32_t), st));
+  PqpSolveArgs a{};
+  a.d = b->d;
+  a.p = b->p;
+  a.lay = b->lay;
+  a.batch = (int32_t)b->B;
+  a.counter = b->counter;
+  a.ws = b->ws;
+  a.dbg = b->dbg;
+  a.dbg_cap = b->dbg_cap;
+  a.dbg_qp = 0;
+  if (const char* e = std::getenv("PQP_DEBUG_TRACE")) a.dbg_qp = std::atoi(e);
+  CUDA_TRY(cudaEventRecord(b->ev2, st));
+  int rc = pqp_launch_solve(&a, b->grid, st);
+  if (rc != 0) return fail(PQP_ECUDA, std::string("solve kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+  CUDA_TRY(cudaEventRecord(b->ev3, st));
+  b->solve_timed = true;
+  b->launches += 1;
+  b->solve_pending = true;
+  for (int64_t i = 0; i < b->B; ++i) {
+    if (b->hparams[i].active) {
+      b->flags[i].dirty = true; // solver.hpp:1835-1836
+      b->flags[i].is_initialized = true;
+    }
+  }
+  return 0;
+}
+
+int
+pqp_batch_sync(pqp_batch* b)
+{
+  if (!b) return fail(PQP_EINVAL, "null batch");
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (b->solve_pending) {
+    std::vector<double> raw((size_t)b->B * PQP_INFO_DOUBLES);
+    CUDA_TRY(cudaMemcpy(raw.data(), b->p.info, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost));
+    float ms_solve = 0, ms_setup = 0;
+    if (b->solve_timed) cudaEventElapsedTime(&ms_solve, b->ev2, b->ev3);
+    if (b->setup_timed) cudaEventElapsedTime(&ms_setup, b->ev0, b->ev1);
+    int64_t nact = 0;
+    for (int64_t i = 0; i < b->B; ++i) nact += b->hparams[i].active ? 1 : 0;
+    for (int64_t i = 0; i < b->B; ++i) {
+      if (!b->hparams[i].active) continue;
+      const double* I = raw.data() + (size_t)i * PQP_INFO_DOUBLES;
+      pqp_info& o = b->hinfo[i];
+      o.mu_eq = I[0];
+      o.mu_eq_inv = I[1];
+      o.mu_in = I[2];
+      o.mu_in_inv = I[3];
+      o.rho = I[4];
+      o.nu = I[5];
+      o.iter = (int64_t)I[6];
+      o.iter_ext = (int64_t)I[7];
+      o.mu_updates = (int64_t)I[8];
+      o.rho_updates = (int64_t)I[9];
+      o.status = (int64_t)I[10];
+      o.objValue = I[14];
+      o.pri_res = I[15];
+      o.dua_res = I[16];
+      o.duality_gap = I[17];
+      o.iterative_residual = I[18];
+      if (b->hparams[i].s.compute_timings && nact > 0) {
+        // microseconds; the batch runs as one kernel, so per-QP time = batch time / batch size
+        o.solve_time = 1e3 * ms_solve / double(nact);
+        o.setup_time = 1e3 * ms_setup / double(nact);
+        o.run_time = o.solve_time + o.setup_time;
+      }
+    }
+    b->solve_pending = false;
+  }
+  return 0;
+}
+
+int
+pqp_batch_solve(pqp_batch* b)
+{
+  if (int rc = pqp_batch_solve_async(b, nullptr)) return rc;
+  return pqp_batch_sync(b);
+}
+
+int
+pqp_batch_results(pqp_batch* b, int64_t first, int64_t count, double* x, double* y, double* z, double* se, double* si, pqp_info* info)
+{
+  if (int rc = check_range(b, first, count)) return rc;
+  if (int rc = pqp_batch_sync(b)) return rc;
+  const PqpDims& d = b->d;
+  auto out = [&](double* dst, const double* src, int64_t per) -> int {
+    if (!dst || per == 0 || count == 0) return 0;
+    CUDA_TRY(cudaMemcpy(dst, src + first * per, sizeof(double) * (size_t)(count * per), cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  if (int rc = out(x, b->p.x, d.n)) return rc;
+  if (int rc = out(y, b->p.y, d.ne)) return rc;
+  if (int rc = out(z, b->p.z, d.nc)) return rc;
+  if (int rc = out(se, b->p.se, d.ne)) return rc;
+  if (int rc = out(si, b->p.si, d.nc)) return rc;
+  if (info) {
+    for (int64_t i = 0; i < count; ++i) info[i] = b->hinfo[first + i];
+  }
+  return 0;
+}
+
+int
+pqp_batch_results_device(pqp_batch* b, double** x, double** y, double** z, double** info20)
+{
+  if (!b) return fail(PQP_EINVAL, "null batch");
+  if (x) *x = b->p.x;
+  if (y) *y = b->p.y;
+  if (z) *z = b->p.z;
+  if (info20) *info20 = b->p.info;
+  return 0;
+}
+
+int
+pqp_batch_scaled(pqp_batch* b, int64_t index, double* H, double* g, double* A, double* b_, double* C, double* u, double* l, double* delta, double* c)
+{
+  if (int rc = check_range(b, index, 1)) return rc;
+  CUDA_TRY(cudaSetDevice(b->device));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
+  const PqpDims& d = b->d;
+  const size_t n = d.n, ne = d.ne, ni = d.ni, nc = d.nc, i = (size_t)index;
+  auto out = [&](double* dst, const double* src, size_t per) -> int {
+    if (!dst || per == 0) return 0;
+    CUDA_TRY(cudaMemcpy(dst, src + i * per, sizeof(double) * per, cudaMemcpyDeviceToHost));
+    return 0;
+  };
+  if (int rc = out(H, b->p.Hs, n * n)) return rc;
+  if (int rc = out(g, b->p.gs, n)) return rc;
+  if (int rc = out(A, b->p.As, ne * n)) return rc;
+  if (int rc = out(b_, b->p.bs, ne)) return rc;
+  if (int rc = out(C, b->p.Cs, ni * n)) return rc;
+  if (int rc = out(u, b->p.us, nc)) return rc;
+  if (int rc = out(l, b->p.ls, nc)) return rc;
+  if (int rc = out(delta, b->p.delta, n + ne + nc)) return rc;
+  if (int rc = out(c, b->p.c, 1)) return rc;
+  return 0;
+}
+
+int
+pqp_batch_cleanup(pqp_batch* b, int64_t first, int64_t count)
+{
+  if (int rc = check_range(b, first, count)) return rc;
+  CUDA_TRY(cudaSetDevice(b->device));
+  for (int64_t i = first; i < first + count; ++i) {
+    if (int rc = zero_results(b, i)) return rc;
+    cold_start(b->hinfo[i], &b->hparams[i].s, b->backend);
+    b->flags[i] = QpFlags(); // workspace.hpp:330-377
+  }
+  return 0;
+}
+
+int
+pqp_batch_timings(const pqp_batch* b, double* setup_ms, double* solve_ms, int64_t* launches)
+{
+  if (!b) return fail(PQP_EINVAL, "null batch");
+  float ms = 0;
+  if (setup_ms) {
+    *setup_ms = 0;
+    if (b->setup_timed && cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) *setup_ms = ms;
+  }
+  if (solve_ms) {
+    *solve_ms = 0;
+    if (b->solve_timed && cudaEventElapsedTime(&ms, b->ev2, b->ev3) == cudaSuccess) *solve_ms = ms;
+  }
+  if (launches) *launches = b->launches;
+  return 0;
+}
+
+// debug trace access (PQP_DEBUG_TRACE=<qp index> in the environment)
+int
+pqp_batch_debug_trace(pqp_batch* b, double* out, int64_t cap)
+{
+  if (!b || !b->dbg) return 0;
+  cudaMemcpy(out, b->dbg, sizeof(double) * (size_t)std::min<int64_t>(cap, b->dbg_cap), cudaMemcpyDeviceToHost);
+  return (int)std::min<int64_t>(cap, b->dbg_cap);
+}
+
+int
+pqp_batch_launch_config(const pqp_batch* b, int* grid, int* smem_bytes, int* in_smem_mask, int64_t* ws_doubles)
+{
+  if (!b) return fail(PQP_EINVAL, "null batch");
+  if (grid) *grid = b->grid;
+  if (smem_bytes) *smem_bytes = (int)(sizeof(double) * (size_t)b->lay.smem_doubles + (size_t)b->lay.smem_int_bytes);
+  if (in_smem_mask) {
+    int m = 0;
+    for (int i = 0; i < PA_COUNT; ++i) m |= (b->lay.in_smem[i] ? 1 : 0) << i;
+    *in_smem_mask = m;
+  }
+  if (ws_doubles) *ws_doubles = b->lay.ws_doubles;
+  return 0;
+}
+
+int
+pqp_random_qp(int kind, uint64_t seed, int64_t dim, int64_t n_eq, int64_t n_in, double sparsity, double strong_convexity, double* H, double* g, double* A, double* b_, double* C, double* u, double* l, double* u_box, double* l_box)
+{
+  pqp::randqp::Lehmer rng;
+  rng.set_seed(seed);
+  const int n = (int)dim, ne = (int)n_eq, ni = (int)n_in;
+  switch (kind) {
+    case 0: pqp::randqp::dense_strongly_convex_qp(rng, n, ne, ni, sparsity, strong_convexity, H, g, A, b_, C, u, l); return 0;
+    case 1: pqp::randqp::dense_not_strongly_convex_qp(rng, n, ne, ni, sparsity, H, g, A, b_, C, u, l); return 0;
+    case 2: pqp::randqp::dense_degenerate_qp(rng, n, ne, ni, sparsity, strong_convexity, H, g, A, b_, C, u, l); return 0;
+    case 3: pqp::randqp::dense_box_constrained_qp(rng, n, ne, ni, sparsity, strong_convexity, H, g, A, b_, C, u, l); return 0;
+    case 4: pqp::randqp::dense_box_benchmark_qp(rng, n, ne, ni, sparsity, strong_convexity, 0, H, g, A, b_, C, u, l, u_box, l_box); return 0;
+    case 5: pqp::randqp::dense_box_benchmark_qp(rng, n, ne, ni, sparsity, strong_convexity, 1, H, g, A, b_, C, u, l, u_box, l_box); return 0;
+  }
+  return fail(PQP_EINVAL, "unknown generator kind");
+}
+
+} // extern "C"

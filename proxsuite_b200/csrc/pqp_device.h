@@ -1,0 +1,132 @@
+// Shared host/device declarations of the B200 batched dense ProxQP kernels.
+//
+// Data layout in HBM (all fp64, batch-major, every matrix row-major — the
+// reference's layout, dense/fwd.hpp:16-33):
+//   model   : H[B][n*n] g[B][n] A[B][ne*n] b[B][ne] C[B][ni*n] l,u[B][ni] l_box,u_box[B][n]
+//             (copies of the caller's data, reference helpers.hpp:573-612)
+//   scaled  : Hs, gs, As, bs, Cs, us, ls [B][ncons] (constraint order: C rows then box), is[B][n]
+//             delta[B][n+ne+ncons], c[B]          (workspace.hpp:35-44, ruiz.hpp:319-320)
+//   results : x[B][n] y[B][ne] z[B][ncons] se[B][ne] si[B][ncons] info[B][20]
+//   params  : one PqpQpParams per QP (settings + proximal parameters + start mode)
+// Per-CTA (not per-QP) scratch lives in a global workspace that stays
+// L2-resident: the Gram matrix G of constraint rows, temporaries, and any of
+// the factor arrays that do not fit in shared memory.
+#pragma once
+#include "../../include/pqp.h"
+#include <stdint.h>
+
+#define PQP_NT 256          // threads per CTA (8 warps = one warp-group pair per QP)
+#define PQP_NW (PQP_NT / 32)
+#define PQP_INFO_DOUBLES 20
+
+// start modes derived on the host from settings.initial_guess and the
+// init/update/solve state machine (solver.hpp:1125-1377)
+enum PqpStartMode {
+  PQP_START_COLD = 0,        // x = y = z = 0 (NO_INITIAL_GUESS)
+  PQP_START_EQ_GUESS = 1,    // + equality constrained initial guess (helpers.hpp:201-228)
+  PQP_START_WARM = 2,        // x, y, z from results (unscaled), proximal parameters reset
+  PQP_START_WARM_KEEP = 3    // WARM_START_WITH_PREVIOUS_RESULT: keep rho / mu as they are
+};
+
+struct PqpQpParams
+{
+  pqp_settings s;
+  double rho, mu_eq, mu_in; // proximal parameters to start from (results.info)
+  int32_t start_mode;
+  int32_t active;           // 0: skip this QP (not initialised)
+};
+
+struct PqpDims
+{
+  int n, ne, ni, nc; // nc = ni + (box ? n : 0)
+  int box, hess;
+  int cap;           // ne + nc : capacity of the dual block
+};
+
+struct PqpBatchPtrs
+{
+  // model (unscaled)
+  double *H, *g, *A, *b, *C, *l, *u, *l_box, *u_box;
+  // scaled
+  double *Hs, *gs, *As, *bs, *Cs, *us, *ls, *is;
+  double *delta, *c;
+  // results
+  double *x, *y, *z, *se, *si, *info;
+  PqpQpParams* params;
+};
+
+// Arrays the solve kernel places either in shared memory or in the per-CTA
+// global workspace (decided on the host, see pqp_layout.cpp).
+enum PqpArr {
+  PA_M1 = 0,   // strict lower packed inverse factor of P = Hs + rho I : n(n-1)/2
+  PA_AS,       // scaled equality matrix ne x n
+  PA_MS,       // strict lower packed inverse factor of the dual Schur block : cap(cap-1)/2
+  PA_G,        // packed lower (with diagonal) Gram matrix B P^-1 B^T by row id : cap(cap+1)/2
+  PA_Y,        // n x max(ne, 1) temporary (P^-1 A^T)
+  PA_VEC,      // all vectors, one arena (sub-offsets below)
+  PA_COUNT
+};
+
+// vector sub-arena (offsets in doubles from the arena base)
+enum PqpVec {
+  V_X = 0, V_Y, V_Z, V_XP, V_YP, V_ZP,
+  V_DX, V_DS, V_DZ,          // dw: x part, dual slots part, dz in constraint order
+  V_RX, V_RS,                // rhs
+  V_EX, V_ES,                // err
+  V_DUAL, V_SE, V_RUP, V_SI,
+  V_HDX, V_ADX, V_ATDY, V_CDX, V_CTDZ, V_Q,
+  V_GS, V_BS, V_US, V_LS, V_IS, V_DELTA,
+  V_B, V_U, V_L,             // unscaled b, u, l (u, l in constraint order incl. box)
+  V_D1INV, V_DSV, V_DSINV,
+  V_T1, V_T2, V_T3,          // n-sized temporaries
+  V_S1, V_S2, V_S3, V_S4,    // cap-sized temporaries
+  V_ALPHAS, V_GRADS,         // 2*nc + 2
+  V_SCRATCH,                 // partial-sum scratch
+  V_RED,                     // reduction scratch (64)
+  V_COUNT
+};
+
+struct PqpLayout
+{
+  int64_t off[PA_COUNT];      // offset in doubles inside smem or the CTA workspace
+  int32_t in_smem[PA_COUNT];
+  int32_t voff[V_COUNT];      // offsets inside the vector arena
+  int32_t vec_doubles;
+  int32_t scratch_doubles;
+  int32_t smem_doubles;       // total doubles of dynamic shared memory
+  int32_t smem_int_bytes;     // bytes of int scratch that follow the doubles
+  int64_t ws_doubles;         // per-CTA global workspace in doubles
+};
+
+struct PqpSolveArgs
+{
+  PqpDims d;
+  PqpBatchPtrs p;
+  PqpLayout lay;
+  int32_t batch;
+  int32_t* counter;  // dynamic work queue (replaces OpenMP schedule(dynamic), qp_solve.hpp:55)
+  double* ws;        // per-CTA workspace base
+  double* dbg;       // optional debug trace buffer (NULL = off)
+  int32_t dbg_qp;
+  int32_t dbg_cap;
+};
+
+struct PqpSetupArgs
+{
+  PqpDims d;
+  PqpBatchPtrs p;
+  int32_t first, count;
+  int32_t execute;           // 1: run Ruiz (EXECUTE); 0: apply stored delta/c (KEEP / IDENTITY)
+  int32_t reset_scaling;     // 1: set delta = 1, c = 1 first (IDENTITY)
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+// host-side launchers implemented in pqp_kernels.cu
+int pqp_launch_setup(const PqpSetupArgs* a, void* stream);
+int pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream);
+int pqp_solve_max_smem(void);
+#ifdef __cplusplus
+}
+#endif
