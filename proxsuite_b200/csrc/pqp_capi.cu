@@ -752,6 +752,7 @@ pqp_batch_solve_async(pqp_batch* b, void* stream_)
   a.dbg_cap = b->dbg_cap;
   a.dbg_qp = 0;
   if (const char* e = std::getenv("PQP_DEBUG_TRACE")) a.dbg_qp = std::atoi(e);
+  if (const char* e = std::getenv("PQP_WATCHDOG_MS")) a.watchdog_ns = 1000000ull * (unsigned long long)std::atoll(e);
   CUDA_TRY(cudaEventRecord(b->ev2, st));
   int rc = pqp_launch_solve(&a, b->grid, st);
   if (rc != 0) return fail(PQP_ECUDA, std::string("solve kernel launch: ") + cudaGetErrorString((cudaError_t)rc));

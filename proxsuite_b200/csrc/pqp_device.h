@@ -109,6 +109,7 @@ struct PqpSolveArgs
   double* dbg;       // optional debug trace buffer (NULL = off)
   int32_t dbg_qp;
   int32_t dbg_cap;
+  unsigned long long watchdog_ns; // 0 = off; per-QP time budget after which the QP is abandoned (status MAX_ITER_REACHED)
 };
 
 struct PqpSetupArgs

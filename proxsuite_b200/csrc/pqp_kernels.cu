@@ -184,19 +184,26 @@ __device__ void tri_mv_impl(const double* __restrict__ M, const double* __restri
 {
   const int sub = threadIdx.x / LPR, sl = threadIdx.x % LPR;
   constexpr int NSUB = NT / LPR;
-  for (int i = sub; i < n; i += NSUB) {
-    const double* row = M + tri_off(i);
-    double a0 = 0, a1 = 0;
-    int j = sl;
-    for (; j + LPR < i; j += 2 * LPR) {
-      a0 += row[j] * x[j];
-      a1 += row[j + LPR] * x[j + LPR];
+  // the trip count is uniform over the CTA: sub-groups of one warp own
+  // different rows, and every lane must take part in the shuffles below
+  for (int i0 = 0; i0 < n; i0 += NSUB) {
+    const int i = i0 + sub;
+    const bool valid = i < n;
+    double acc = 0;
+    if (valid) {
+      const double* row = M + tri_off(i);
+      double a0 = 0, a1 = 0;
+      int j = sl;
+      for (; j + LPR < i; j += 2 * LPR) {
+        a0 += row[j] * x[j];
+        a1 += row[j + LPR] * x[j + LPR];
+      }
+      if (j < i) a0 += row[j] * x[j];
+      acc = a0 + a1;
     }
-    if (j < i) a0 += row[j] * x[j];
-    double acc = a0 + a1;
 #pragma unroll
     for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-    if (sl == 0) {
+    if (valid && sl == 0) {
       double v = acc + x[i];
       y[i] = scale ? v * scale[i] : v;
     }
@@ -971,6 +978,13 @@ __device__ double primal_dual_ls(Ctx& c, const Scal& sc, const pqp_settings& S)
   return fabs(alpha_last_neg - last_neg_grad * (alpha_first_pos - alpha_last_neg) / (first_pos_grad - last_neg_grad));
 }
 
+__device__ __forceinline__ unsigned long long gtimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ void dbg_write(const PqpSolveArgs& A, int q, int& pos, double a, double b, double c0, double d, double e, double f)
 {
   if (A.dbg && q == A.dbg_qp && threadIdx.x == 0 && pos + 6 <= A.dbg_cap) {
@@ -1130,6 +1144,8 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
   }(); // |model.g|_inf (helpers.hpp:651)
   double info_pri = 0, info_dua = 0, info_gap = 0;
   bool infeasible_exit = false;
+  bool expired = false; // watchdog (debug aid, off by default)
+  const unsigned long long t_start = A.watchdog_ns ? gtimer_ns() : 0ull;
 
   for (long long iter = 0; iter < S.max_iter; ++iter) {
     global_primal_residual(c, sc, S, g);
@@ -1182,6 +1198,13 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
         if (it_in == S.max_iter_in) {
           sc.iter += S.max_iter_in + 1;
           break;
+        }
+        if (A.watchdog_ns) {
+          if (tid == 0) c.iscratch[2 * NW + 1] = (gtimer_ns() - t_start > A.watchdog_ns) ? 1 : 0;
+          __syncthreads();
+          expired = c.iscratch[2 * NW + 1] != 0;
+          __syncthreads();
+          if (expired) break;
         }
         // -- Newton step (solver.hpp:756-869)
         for (int i = tid; i < nc; i += NT) {
@@ -1325,6 +1348,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
         }
       }
     }
+    if (expired) break;
     if ((sc.status == PQP_PRIMAL_INFEASIBLE && !S.primal_infeasibility_solving) || sc.status == PQP_DUAL_INFEASIBLE) {
       // certificate of infeasibility: the (already unscaled, quirk 4) step
       for (int j = tid; j < n; j += NT) c.x[j] = c.dx[j] * dlx[j];

@@ -15,7 +15,7 @@ that `solve_in_parallel` is ONE persistent-kernel launch per shape.
 """
 from __future__ import annotations
 
-import ctypes as C
+import ctypes as ct
 from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -23,7 +23,7 @@ import numpy as np
 from .. import _capi
 from . import DenseBackend, HessianType, Info, InitialGuess, Results, Settings
 
-_VP = C.c_void_p
+_VP = ct.c_void_p
 
 
 def _ptr(a):
@@ -59,8 +59,8 @@ def _vec(a, size, what, allow_empty=True):
 def _opt_scalar(v):
     if v is None:
         return None, None
-    c = C.c_double(float(v))
-    return c, C.cast(C.pointer(c), _VP)
+    c = ct.c_double(float(v))
+    return c, ct.cast(ct.pointer(c), _VP)
 
 
 class _Group:
@@ -78,8 +78,8 @@ class _Group:
             if "wrong argument" in msg:
                 raise ValueError(msg)
             raise RuntimeError(f"proxsuite_b200: cannot create device batch: {msg}")
-        be = C.c_int(0)
-        self.lib.pqp_batch_dims(self.handle, None, None, None, None, None, C.cast(C.pointer(be), _VP))
+        be = ct.c_int(0)
+        self.lib.pqp_batch_dims(self.handle, None, None, None, None, None, ct.cast(ct.pointer(be), _VP))
         self.backend = DenseBackend(be.value)
         self.used = 0
         self.members: List["QP"] = []
@@ -96,10 +96,10 @@ class _Group:
 
     # -- settings ---------------------------------------------------------
     def push_settings(self, index, settings: Settings):
-        _capi.check(self.lib.pqp_batch_settings_set(self.handle, index, C.byref(settings._c)))
+        _capi.check(self.lib.pqp_batch_settings_set(self.handle, index, ct.byref(settings._c)))
 
     def pull_settings(self, index, settings: Settings):
-        _capi.check(self.lib.pqp_batch_settings_get(self.handle, index, C.byref(settings._c)))
+        _capi.check(self.lib.pqp_batch_settings_get(self.handle, index, ct.byref(settings._c)))
 
     def push_all(self):
         for q in self.members:
@@ -126,12 +126,12 @@ class _Group:
         se = np.zeros((count, self.n_eq))
         si = np.zeros((count, self.nc))
         info = (_capi.pqp_info * count)()
-        _capi.check(self.lib.pqp_batch_results(self.handle, first, count, _ptr(x), _ptr(y), _ptr(z), _ptr(se), _ptr(si), C.cast(info, _VP)))
+        _capi.check(self.lib.pqp_batch_results(self.handle, first, count, _ptr(x), _ptr(y), _ptr(z), _ptr(se), _ptr(si), ct.cast(info, _VP)))
         return x, y, z, se, si, info
 
     def timings(self):
-        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
-        self.lib.pqp_batch_timings(self.handle, C.cast(C.pointer(a), _VP), C.cast(C.pointer(b), _VP), C.cast(C.pointer(n), _VP))
+        a, b, n = ct.c_double(0), ct.c_double(0), ct.c_int64(0)
+        self.lib.pqp_batch_timings(self.handle, ct.cast(ct.pointer(a), _VP), ct.cast(ct.pointer(b), _VP), ct.cast(ct.pointer(n), _VP))
         return dict(setup_ms=a.value, solve_ms=b.value, kernel_launches=n.value)
 
 
@@ -264,8 +264,8 @@ class QP:
         n, ne, ni, nc = self._n, self._n_eq, self._n_in, self._nc
         H = np.zeros((n, n)); g = np.zeros(n); A = np.zeros((ne, n)); b = np.zeros(ne)
         Cm = np.zeros((ni, n)); u = np.zeros(nc); l = np.zeros(nc); delta = np.zeros(n + ne + nc)
-        c = C.c_double(0)
-        _capi.check(self._group.lib.pqp_batch_scaled(self._group.handle, self._index, _ptr(H), _ptr(g), _ptr(A), _ptr(b), _ptr(Cm), _ptr(u), _ptr(l), _ptr(delta), C.cast(C.pointer(c), _VP)))
+        c = ct.c_double(0)
+        _capi.check(self._group.lib.pqp_batch_scaled(self._group.handle, self._index, _ptr(H), _ptr(g), _ptr(A), _ptr(b), _ptr(Cm), _ptr(u), _ptr(l), _ptr(delta), ct.cast(ct.pointer(c), _VP)))
         return dict(H=H, g=g, A=A, b=b, C=Cm, u=u, l=l, delta=delta, c=c.value)
 
 
@@ -415,7 +415,7 @@ class DenseBatch:
         self.settings = Settings(self._g.backend)
 
     def _push(self):
-        _capi.check(self._g.lib.pqp_batch_settings_set(self._g.handle, -1, C.byref(self.settings._c)))
+        _capi.check(self._g.lib.pqp_batch_settings_set(self._g.handle, -1, ct.byref(self.settings._c)))
 
     def init(self, H=None, g=None, A=None, b=None, C=None, l=None, u=None, l_box=None, u_box=None,
              compute_preconditioner=True, rho=None, mu_eq=None, mu_in=None, manual_minimal_H_eigenvalue=None, update=False):
@@ -438,7 +438,7 @@ class DenseBatch:
         self._push()
         fn = G.lib.pqp_batch_update if update else G.lib.pqp_batch_init
         _capi.check(fn(G.handle, 0, B, *[_ptr(a) for a in arrs], int(compute_preconditioner), *[k[1] for k in keep]))
-        _capi.check(G.lib.pqp_batch_settings_get(G.handle, 0, C.byref(self.settings._c)))
+        _capi.check(G.lib.pqp_batch_settings_get(G.handle, 0, ct.byref(self.settings._c)))
 
     def update(self, **kw):
         kw.setdefault("compute_preconditioner", kw.pop("update_preconditioner", False))
@@ -449,14 +449,14 @@ class DenseBatch:
         xs = [None if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in (x, y, z)]
         self._push()
         _capi.check(G.lib.pqp_batch_warm_start(G.handle, 0, self.batch, *[_ptr(a) for a in xs]))
-        _capi.check(G.lib.pqp_batch_settings_get(G.handle, 0, C.byref(self.settings._c)))
+        _capi.check(G.lib.pqp_batch_settings_get(G.handle, 0, ct.byref(self.settings._c)))
 
     def solve(self, x=None, y=None, z=None):
         if x is not None or y is not None or z is not None:
             self.warm_start(x, y, z)
         self._push()
         _capi.check(self._g.lib.pqp_batch_solve(self._g.handle))
-        _capi.check(self._g.lib.pqp_batch_settings_get(self._g.handle, 0, C.byref(self.settings._c)))
+        _capi.check(self._g.lib.pqp_batch_settings_get(self._g.handle, 0, ct.byref(self.settings._c)))
 
     def solve_async(self, stream=None):
         self._push()
@@ -475,9 +475,9 @@ class DenseBatch:
         return self._g.timings()
 
     def launch_config(self):
-        grid, smem, mask, ws = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int64(0)
+        grid, smem, mask, ws = ct.c_int(0), ct.c_int(0), ct.c_int(0), ct.c_int64(0)
         G = self._g
-        G.lib.pqp_batch_launch_config(G.handle, C.cast(C.pointer(grid), _VP), C.cast(C.pointer(smem), _VP), C.cast(C.pointer(mask), _VP), C.cast(C.pointer(ws), _VP))
+        G.lib.pqp_batch_launch_config(G.handle, ct.cast(ct.pointer(grid), _VP), ct.cast(ct.pointer(smem), _VP), ct.cast(ct.pointer(mask), _VP), ct.cast(ct.pointer(ws), _VP))
         return dict(grid=grid.value, smem_bytes=smem.value, in_smem_mask=mask.value, ws_doubles=ws.value)
 
     def debug_trace(self):
