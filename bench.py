@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — QPs solved per second on batched dense ProxQP (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (GPU arm, this repo)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the reference's
+                                                              algorithm on the host cores)
+
+Workload (BASELINE.json configs[1]): per GPU a BatchQP of 1024 random dense QPs,
+n=100, n_eq=50, n_in=100, fp64, generated exactly like the reference's batch
+benchmark (benchmark/timings-parallel.cpp:19-54: set_seed(i) +
+dense_strongly_convex_qp(sparsity 0.15, strong convexity 1e-2), eps_abs=1e-9,
+eps_rel=0, NO_INITIAL_GUESS). A "step" is one solve_in_parallel over the whole
+(already init-ed) batch — what timings-parallel.cpp:208-232 times. Weak scaling:
+every rank owns its own 1024 QPs, no collective in the data path.
+
+`value`   : QPs/s with inputs resident in HBM, CUDA-event timed on the launching stream.
+`e2e`     : QPs/s through the public API with HOST (pinned) inputs: H2D copy + init
+            (Ruiz set-up kernel) + solve + D2H of x, y, z, se, si, info, every step.
+`roofline`: algorithmic bytes (SURVEY.md section 8(d)(ii) streamed-operand model,
+            evaluated from the oracle's operation counters on a sample of the
+            same workload) / measured solve-kernel time, against the measured
+            HBM peak of MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DIM, N_EQ, N_IN = 100, 50, 100
+BATCH_PER_GPU = 1024
+SPARSITY, STRONG_CONVEXITY = 0.15, 1e-2
+EPS_ABS = 1e-9
+KEYS = "HgAbClu"
+
+
+def algorithmic_bytes_per_qp(cnt, n, ne, ni, ncons, batch):
+    """bytes of the operands each executed primitive
+    streams, from the oracle's counters (mean per QP)."""
+    nnzH = n * n
+    c = {k: v / batch for k, v in cnt.items()}
+    b = 8.0 * c["factor_m2"]
+    b += 8.0 * (c["solve_m2"] + 4.0 * c["solve_m"])
+    b += 8.0 * (c["n_resid"] * (nnzH + 2 * ne * n) + n * c["resid_nc"] + 6.0 * c["solve_m"])
+    b += 16.0 * c["rank_chunk_t2"] + 16.0 * c["rank_rt"]
+    b += c["insert_bytes"]
+    b += 8.0 * c["delete_t2"]
+    b += c["n_cdx"] * 16.0 * ni * n
+    b += c["n_global_res"] * 8.0 * (nnzH + 2 * ne * n + 2 * ni * n)
+    b += 8.0 * c["ls_evals"] * (2 * n + 2 * ne + 5 * ncons)
+    return b
+
+
+def compulsory_bytes_per_qp(n, ne, ni):
+    """inputs read once + solution written once."""
+    return 8.0 * (n * n + ne * n + ni * n + n + ne + 2 * ni) + 8.0 * (n + ne + ni)
+
+
+def generate(first, count, gen):
+    data = [gen("strongly_convex", first + i, N_DIM, N_EQ, N_IN, SPARSITY, STRONG_CONVEXITY) for i in range(count)]
+    return {k: np.stack([d[k] for d in data]) for k in KEYS}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(sample, reps, threads=0):
+    """The oracle (C++ restatement of the reference, kind "port") on the host
+    cores: OpenMP schedule(dynamic) over QPs with all threads, batch already
+    init-ed (benchmark/timings-parallel.cpp:208-232)."""
+    from oracle import oracle as O
+
+    O.build()
+    T = threads or O.omp_max_threads()
+    st = generate(0, sample, O.generate_qp)
+    b = O.OracleBatch(sample, N_DIM, N_EQ, N_IN)
+    for i in range(sample):
+        q = b[i]
+        q.set(eps_abs=EPS_ABS, eps_rel=0, initial_guess=O.NO_INITIAL_GUESS)
+        q.init(**{k: st[k][i] for k in KEYS})
+    b.solve(T)  # warm-up
+    b.counters(reset=True)
+    best = None
+    tot = 0.0
+    for _ in range(reps):
+        t = b.solve(T)
+        tot += t
+        best = t if best is None else min(best, t)
+    cnt = b.counters()
+    cnt = {k: v / reps for k, v in cnt.items()}
+    solved = sum(1 for i in range(sample) if b[i].results().info.status == 0)
+    return dict(qps=sample / best, best_s=best, total_s=tot, cores=T, sample=sample, reps=reps, solved=solved, counters=cnt)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path. The reference itself cannot be
+    compiled here (Eigen 3 absent), so this is the oracle
+    port with every host thread; rank 0 alone runs."""
+    if rank != 0:
+        return
+    sample = 256
+    from oracle import oracle as O
+
+    O.build()
+    T = O.omp_max_threads()
+    st = generate(0, sample, O.generate_qp)
+    b = O.OracleBatch(sample, N_DIM, N_EQ, N_IN)
+    for i in range(sample):
+        q = b[i]
+        q.set(eps_abs=EPS_ABS, eps_rel=0, initial_guess=O.NO_INITIAL_GUESS)
+        q.init(**{k: st[k][i] for k in KEYS})
+    for _ in range(args.warmup):
+        b.solve(T)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b.solve(T)
+    dt = time.perf_counter() - t0
+    qps = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "QPs solved/sec (batch dense, n=100)", "value": qps, "unit": "QPs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BatchQP dense n={N_DIM} n_eq={N_EQ} n_in={N_IN} eps_abs=1e-9 NO_INITIAL_GUESS; step = solve_in_parallel over a {sample}-QP sample of the 1024-QP batch, OpenMP schedule(dynamic)",
+                   "batch_per_step": sample},
+        "cpu_baseline": {"value": qps, "unit": "QPs/s", "cores": T, "kind": "port", "sample": f"{sample} QPs x {args.steps} steps, seeds 0..{sample - 1}"},
+        "e2e": {"value": qps, "unit": "QPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="QPs per GPU (BASELINE.json configs[1]: 1024)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; proxsuite_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    from proxsuite_b200 import proxqp
+
+    B = args.batch
+    n, ne, ni = N_DIM, N_EQ, N_IN
+    # synthetic inputs of this rank (seeds rank*B .. rank*B+B-1), in pinned host memory
+    host = generate(rank * B, B, proxqp.dense.random_qp)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+    host = {k: v.numpy() for k, v in pinned.items()}
+    h2d_bytes = sum(v.nbytes for v in host.values())
+
+    db = proxqp.dense.DenseBatch(B, n, ne, ni, device=local_rank)
+    db.settings.eps_abs = EPS_ABS
+    db.settings.eps_rel = 0
+    db.settings.initial_guess = proxqp.InitialGuess.NO_INITIAL_GUESS
+    db.init(**host)
+    db.solve()
+    chk = db.results()
+    assert (chk["info"]["status"] == 0).all(), "not every QP was solved"
+    x = chk["x"]
+    cx = np.einsum("bij,bj->bi", host["C"], x)
+    pri = max(np.abs(np.einsum("bij,bj->bi", host["A"], x) - host["b"]).max(), np.abs(np.maximum(cx - host["u"], 0) + np.minimum(cx - host["l"], 0)).max())
+    dua = np.abs(np.einsum("bij,bj->bi", host["H"], x) + host["g"] + np.einsum("bji,bj->bi", host["A"], chk["y"]) + np.einsum("bji,bj->bi", host["C"], chk["z"])).max()
+    assert pri <= 1e-9 and dua <= 1e-9, (pri, dua)
+
+    stream = torch.cuda.current_stream()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") --------------------------------
+    for _ in range(args.warmup):
+        db.solve_async(stream.cuda_stream)
+    db.sync()
+    launches0 = db.timings()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        db.solve_async(stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    db.sync()
+    launches = db.timings()["kernel_launches"] - launches0
+    kernel_ms = db.timings()["solve_ms"]  # last solve kernel alone (events around the launch)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the public API ("e2e") ---------------------------
+    def e2e_step():
+        db.init(**host)          # H2D from pinned memory + Ruiz set-up kernel
+        db.solve()               # persistent solve kernel
+        r = db.results()         # D2H of x, y, z, se, si + info
+        if world > 1:            # the one exchange step: gather the solutions
+            tx = torch.from_numpy(r["x"]).cuda()
+            out = [torch.empty_like(tx) for _ in range(world)] if rank == 0 else None
+            dist.gather(tx, out, dst=0)
+        return r
+    d2h_bytes = 8 * B * (n + 2 * ne + 2 * ni) + B * 20 * 8
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        cpu = None
+        b_alg = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(sample=512, reps=5)
+            b_alg = algorithmic_bytes_per_qp(cpu["counters"], n, ne, ni, ni, cpu["sample"])
+        else:
+            try:
+                with open(os.path.join(ROOT, "profiles", "algorithmic_bytes.json")) as f:
+                    b_alg = json.load(f)["bytes_per_qp"]
+            except Exception:
+                b_alg = None
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = None
+        if b_alg is not None and kernel_ms > 0:
+            achieved = b_alg * B / (kernel_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_source": peak_src, "kernel": "pqp_solve_kernel", "kernel_ms": kernel_ms,
+                    "algorithmic_bytes_per_qp": b_alg, "compulsory_bytes_per_qp": compulsory_bytes_per_qp(n, ne, ni),
+                    "achieved_compulsory_gbs": compulsory_bytes_per_qp(n, ne, ni) * B / (kernel_ms * 1e-3) / 1e9}
+        line = {
+            "metric": "QPs solved/sec (batch dense, n=100)", "value": value, "unit": "QPs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BatchQP {B} random dense QPs per GPU, n={n} n_eq={n_eq_str()} n_in={ni}, fp64, eps_abs=1e-9 eps_rel=0 NO_INITIAL_GUESS (BASELINE.json configs[1]; generator of benchmark/timings-parallel.cpp)",
+                       "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"batch sharded over {world} GPU(s), no collective in the iteration",
+                       "l2": "inputs larger than L2 (scaled+model data %.0f MB per GPU per step)" % (2 * h2d_bytes / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "QPs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": None if cpu is None else {"value": cpu["qps"], "unit": "QPs/s", "cores": cpu["cores"], "kind": "port",
+                                                      "sample": f"{cpu['sample']} QPs of the same workload x {cpu['reps']} repetitions (best), OpenMP schedule(dynamic), {cpu['solved']}/{cpu['sample']} solved"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def n_eq_str():
+    return str(N_EQ)
+
+
+if __name__ == "__main__":
+    main()

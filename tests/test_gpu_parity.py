@@ -1,0 +1,299 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called
+through the C-ABI (proxsuite_b200 -> libpqp_b200.so), against the oracle on
+the same seeded inputs, against the committed golden fixtures, and - at
+BASELINE.json's full size - through size-independent properties.
+
+Tolerances (fp64, stated by north_star): KKT residuals recomputed from the
+ORIGINAL data <= eps_abs = 1e-9; |x_gpu - x_oracle|_inf <= 1e-6 max(1,|x|_inf);
+identical status. Nothing here reads /root/reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import kkt_residuals
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KEYS = "HgAbClu"
+EPS = 1e-9
+XTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def px():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from proxsuite_b200 import proxqp
+
+    return proxqp
+
+
+def gpu_solve(px, d, box=False, hessian=None, **settings):
+    n, ne, ni = d["H"].shape[0], d["A"].shape[0], d["C"].shape[0]
+    hessian = px.HessianType.Dense if hessian is None else hessian
+    qp = px.dense.QP(n, ne, ni, box, hessian)
+    qp.settings.eps_abs = EPS
+    qp.settings.eps_rel = 0
+    for k, v in settings.items():
+        setattr(qp.settings, k, v)
+    args = [d[k] for k in KEYS]
+    if box:
+        args += [d["l_box"], d["u_box"]]
+    qp.init(*args)
+    qp.solve()
+    return qp
+
+
+def oracle_solve(oracle, d, box=False, hessian=1, **settings):
+    n, ne, ni = d["H"].shape[0], d["A"].shape[0], d["C"].shape[0]
+    qp = oracle.OracleQP(n, ne, ni, box_constraints=box, hessian_type=int(hessian))
+    qp.set(eps_abs=EPS, eps_rel=0, **{k: int(v) if not isinstance(v, float) else v for k, v in settings.items()})
+    kw = {k: d[k] for k in KEYS}
+    if box:
+        kw.update(l_box=d["l_box"], u_box=d["u_box"])
+    qp.init(**kw)
+    return qp, qp.solve()
+
+
+def assert_parity(d, r, ro):
+    assert int(r.info.status) == ro.info.status
+    pri, dua = kkt_residuals(d, r.x, r.y, r.z)
+    assert pri <= EPS and dua <= EPS, (pri, dua)
+    assert np.abs(r.x - ro.x).max() <= XTOL * max(1.0, np.abs(ro.x).max())
+    assert np.abs(r.y - ro.y).max() <= 1e-5 * max(1.0, np.abs(ro.y).max())
+    assert np.abs(r.z - ro.z).max() <= 1e-5 * max(1.0, np.abs(ro.z).max())
+
+
+def test_reference_known_answers(px):
+    with open(os.path.join(HERE, "golden", "kat_reference.json")) as f:
+        kats = json.load(f)
+    for k in kats:
+        qp = px.dense.QP(k["n"], k["n_eq"], k["n_in"])
+        qp.init(np.array(k["H"]), np.array(k["g"]), None, None, np.array(k["C"]), np.array(k["l"]), np.array(k["u"]))
+        qp.settings.eps_abs = k["eps_abs"]
+        qp.settings.eps_rel = 0
+        qp.solve()
+        assert int(qp.results.info.status) == k["status"], k["name"]
+        if k["x"] is not None:
+            assert np.allclose(qp.results.x, k["x"], atol=k["tol"]), k["name"]
+
+
+def test_golden_oracle_fixtures(px):
+    with open(os.path.join(HERE, "golden", "oracle_small.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        d = {k: np.array(v) for k, v in c["data"].items()}
+        qp = gpu_solve(px, d, box=c["box"], hessian=px.HessianType(c["hessian"]), initial_guess=px.InitialGuess.NO_INITIAL_GUESS)
+        r = qp.results
+        assert int(r.info.status) == c["status"]
+        assert np.abs(r.x - np.array(c["x"])).max() <= XTOL * max(1.0, np.abs(c["x"]).max()), c["kind"]
+        pri, dua = kkt_residuals(d, r.x, r.y, r.z)
+        assert pri <= EPS and dua <= EPS
+        s = qp.scaled()
+        assert np.allclose(s["delta"], c["delta"], rtol=1e-12, atol=0)
+        assert abs(s["c"] - c["c"]) <= 1e-12
+
+
+@pytest.mark.parametrize("kind,n,ne,ni", [
+    ("strongly_convex", 10, 5, 5), ("strongly_convex", 35, 8, 8), ("strongly_convex", 110, 27, 27),
+    ("strongly_convex", 30, 15, 0), ("strongly_convex", 30, 0, 0), ("strongly_convex", 30, 0, 40),
+    ("box_constrained", 40, 0, 40), ("not_strongly_convex", 40, 20, 20), ("degenerate", 40, 10, 10),
+])
+def test_parity_with_oracle_on_seeded_generators(px, oracle, kind, n, ne, ni):
+    # test/src/dense_qp_with_eq_and_in.cpp, dense_qp_eq.cpp, dense_unconstrained_qp.cpp
+    for seed in (1, 2):
+        d = oracle.generate_qp(kind, seed, n, ne, ni)
+        for ig in (px.InitialGuess.NO_INITIAL_GUESS, px.InitialGuess.EQUALITY_CONSTRAINED_INITIAL_GUESS):
+            qp = gpu_solve(px, d, initial_guess=ig)
+            _, ro = oracle_solve(oracle, d, initial_guess=ig)
+            assert_parity(d, qp.results, ro)
+
+
+def test_ruiz_identity_and_oracle_scaling(px, oracle):
+    # test/src/dense_ruiz_equilibration.cpp:63-71
+    d = oracle.generate_qp("strongly_convex", 1, 40, 20, 20)
+    qp = px.dense.QP(40, 20, 20)
+    qp.init(*[d[k] for k in KEYS])
+    s = qp.scaled()
+    D, E, F, c = s["delta"][:40], s["delta"][40:60], s["delta"][60:80], s["c"]
+    assert np.allclose(s["H"], c * (D[:, None] * d["H"] * D[None, :]), atol=1e-10)
+    assert np.allclose(s["g"], c * D * d["g"], atol=1e-10)
+    assert np.allclose(s["A"], E[:, None] * d["A"] * D[None, :], atol=1e-10)
+    assert np.allclose(s["b"], E * d["b"], atol=1e-10)
+    assert np.allclose(s["C"], F[:, None] * d["C"] * D[None, :], atol=1e-10)
+    oq = oracle.OracleQP(40, 20, 20)
+    oq.init(**{k: d[k] for k in KEYS})
+    so = oq.scaled()
+    for k in ("H", "g", "A", "b", "C", "delta"):
+        assert np.allclose(s[k], so[k], rtol=1e-13, atol=1e-15), k
+    # identity preconditioner
+    qp2 = px.dense.QP(40, 20, 20)
+    qp2.init(*[d[k] for k in KEYS], False)
+    s2 = qp2.scaled()
+    assert np.array_equal(s2["H"], d["H"]) and np.all(s2["delta"] == 1.0) and s2["c"] == 1.0
+
+
+def test_box_constraints_and_z_ordering(px, oracle):
+    # test/src/dense_qp_wrapper.cpp:6803-6900
+    for seed in range(6):
+        d = oracle.generate_qp("box_benchmark", seed, 15, 5, 5, sparsity=0.5)
+        qp = gpu_solve(px, d, box=True)
+        _, ro = oracle_solve(oracle, d, box=True)
+        assert qp.results.z.shape[0] == 5 + 15
+        assert_parity(d, qp.results, ro)
+
+
+def test_diagonal_hessian_and_lp(px, oracle):
+    d = oracle.generate_qp("diagonal_benchmark", 1, 30, 15, 15, sparsity=0.5)
+    qp = gpu_solve(px, d, box=True, hessian=px.HessianType.Diagonal, initial_guess=px.InitialGuess.NO_INITIAL_GUESS)
+    _, ro = oracle_solve(oracle, d, box=True, hessian=2, initial_guess=0)
+    assert_parity(d, qp.results, ro)
+    # LP with HessianType::Zero
+    d = oracle.generate_qp("box_constrained", 3, 20, 5, 20)
+    d["H"] = np.zeros((20, 20))
+    qp = gpu_solve(px, d, hessian=px.HessianType.Zero)
+    _, ro = oracle_solve(oracle, d, hessian=0)
+    assert_parity(d, qp.results, ro)
+
+
+def test_initial_guess_modes_resolve_and_update(px, oracle):
+    # test/src/dense_qp_wrapper.cpp:163-2960; dense_maros_meszaros.cpp:160-162
+    d = oracle.generate_qp("strongly_convex", 1, 20, 5, 10)
+    for ig in px.InitialGuess:
+        if ig == px.InitialGuess.WARM_START:
+            continue
+        qp = gpu_solve(px, d, initial_guess=ig)
+        _, ro = oracle_solve(oracle, d, initial_guess=ig)
+        assert_parity(d, qp.results, ro)
+        qp.solve()  # dirty re-solve
+        r2 = qp.results
+        pri, dua = kkt_residuals(d, r2.x, r2.y, r2.z)
+        assert int(r2.info.status) == 0 and pri <= EPS and dua <= EPS
+        if ig == px.InitialGuess.WARM_START_WITH_PREVIOUS_RESULT:
+            assert r2.info.iter == 0
+    # warm start from the solution through solve(x, y, z): sticky WARM_START
+    qp = gpu_solve(px, d)
+    r = qp.results
+    qp2 = px.dense.QP(20, 5, 10)
+    qp2.settings.eps_abs = EPS
+    qp2.settings.eps_rel = 0
+    qp2.init(*[d[k] for k in KEYS])
+    qp2.solve(r.x, r.y, r.z)
+    assert int(qp2.results.info.status) == 0 and qp2.results.info.iter <= 1
+    assert qp2.settings.initial_guess == px.InitialGuess.WARM_START
+    # update of g, then of H with a fresh preconditioner
+    d2 = dict(d)
+    d2["g"] = d["g"] + 1.0
+    qp.update(g=d2["g"])
+    qp.solve()
+    oq, _ = oracle_solve(oracle, d)
+    oq.update(g=d2["g"])
+    ro = oq.solve()
+    assert_parity(d2, qp.results, ro)
+    d3 = dict(d2)
+    d3["H"] = d["H"] + np.eye(20)
+    qp.update(H=d3["H"], update_preconditioner=True)
+    qp.solve()
+    oq.update(H=d3["H"], update_preconditioner=True)
+    ro = oq.solve()
+    assert_parity(d3, qp.results, ro)
+
+
+def test_parameter_plumbing_and_settings_variants(px, oracle):
+    # test/src/dense_qp_solve.cpp:164 (info.rho == 1e-7)
+    d = oracle.generate_qp("strongly_convex", 1, 10, 2, 2)
+    qp = px.dense.QP(10, 2, 2)
+    qp.settings.eps_abs = EPS
+    qp.init(*[d[k] for k in KEYS], True, 1e-7, 1e-4)
+    qp.solve()
+    assert qp.results.info.rho == 1e-7 and int(qp.results.info.status) == 0
+    # PDAL merit function, Martinez update, duality-gap check
+    d = oracle.generate_qp("strongly_convex", 2, 25, 8, 12)
+    for st in (dict(merit_function_type=px.MeritFunctionType.PDAL), dict(bcl_update=False), dict(check_duality_gap=True)):
+        qp = gpu_solve(px, d, **st)
+        _, ro = oracle_solve(oracle, d, **st)
+        assert_parity(d, qp.results, ro)
+
+
+def test_primal_infeasibility_is_detected(px):
+    # test/src/dense_qp_eq.cpp:217-258
+    H = 2 * np.eye(2)
+    g = np.array([-18.0, -12.0])
+    C = np.array([[1.0, 0.0], [0.0, 1.0], [-1.0, 0.0]])
+    qp = px.dense.QP(2, 0, 3)
+    qp.init(H, g, None, None, C, np.full(3, -np.inf), np.array([10.0, 10.0, -20.0]))
+    qp.settings.eps_abs = EPS
+    qp.settings.eps_rel = 0
+    qp.solve()
+    assert qp.results.info.status == px.QPSolverOutput.PROXQP_PRIMAL_INFEASIBLE
+
+
+def test_batch_equals_serial_bitwise(px, oracle):
+    # test/src/parallel_qp_solve.cpp:19-133 (scaled down: 24 QPs, dim 60)
+    B, n, ne, ni = 24, 60, 10, 10
+    data = [oracle.generate_qp("strongly_convex", i, n, ne, ni) for i in range(B)]
+    batch = px.dense.BatchQP(B)
+    singles = px.dense.VectorQP()
+    for d in data:
+        for qp in (batch.init_qp_in_place(n, ne, ni), singles.init_qp(n, ne, ni)):
+            qp.settings.eps_abs = EPS
+            qp.settings.eps_rel = 0
+            qp.init(*[d[k] for k in KEYS])
+    px.dense.solve_in_parallel(batch)
+    for q in singles:
+        q.solve()
+    assert batch.size() == B
+    for i in range(B):
+        assert np.array_equal(batch.get(i).results.x, singles[i].results.x)
+        assert batch[i].results.info.iter == singles[i].results.info.iter
+    px.dense.solve_in_parallel(singles, 4)  # vector overload, num_threads accepted
+
+
+def test_free_solve_function_and_errors(px, oracle):
+    d = oracle.generate_qp("strongly_convex", 1, 12, 4, 6)
+    r = px.dense.solve(d["H"], d["g"], d["A"], d["b"], d["C"], d["l"], d["u"], eps_abs=EPS, eps_rel=0)
+    pri, dua = kkt_residuals(d, r.x, r.y, r.z)
+    assert int(r.info.status) == 0 and pri <= EPS and dua <= EPS
+    qp = px.dense.QP(12, 4, 6)
+    with pytest.raises(ValueError):  # wrapper.hpp:380-451
+        qp.init(d["H"][:5, :5], d["g"], d["A"], d["b"], d["C"], d["l"], d["u"])
+    with pytest.raises(ValueError):  # box inputs on a QP built without box constraints (wrapper.hpp:540-545)
+        qp.init(d["H"], d["g"], d["A"], d["b"], d["C"], d["l"], d["u"], np.zeros(12), np.ones(12))
+
+
+def test_full_size_batch_properties(px):
+    """BASELINE.json headline shape (n=100, n_eq=50, n_in=100), B=4096: every QP
+    SOLVED with recomputed residuals <= 1e-9; solving the batch twice gives
+    bit-identical results (determinism); permuting the batch permutes the results."""
+    B, n, ne, ni = 4096, 100, 50, 100
+    data = [px.dense.random_qp("strongly_convex", i, n, ne, ni) for i in range(B)]
+    st = {k: np.stack([d[k] for d in data]) for k in KEYS}
+
+    def run(order):
+        db = px.dense.DenseBatch(B, n, ne, ni)
+        db.settings.eps_abs = EPS
+        db.settings.eps_rel = 0
+        db.settings.initial_guess = px.InitialGuess.NO_INITIAL_GUESS
+        db.init(**{k: st[k][order] for k in KEYS})
+        db.solve()
+        return db, db.results()
+
+    ident = np.arange(B)
+    db, r = run(ident)
+    assert (r["info"]["status"] == 0).all()
+    x, y, z = r["x"], r["y"], r["z"]
+    cx = np.einsum("bij,bj->bi", st["C"], x)
+    pri = np.maximum(np.abs(np.einsum("bij,bj->bi", st["A"], x) - st["b"]).max(1),
+                     np.abs(np.maximum(cx - st["u"], 0) + np.minimum(cx - st["l"], 0)).max(1))
+    dua = np.abs(np.einsum("bij,bj->bi", st["H"], x) + st["g"] + np.einsum("bji,bj->bi", st["A"], y) + np.einsum("bji,bj->bi", st["C"], z)).max(1)
+    assert pri.max() <= EPS and dua.max() <= EPS
+    db.solve()
+    r2 = db.results()
+    assert np.array_equal(r2["x"], x)
+    perm = np.random.default_rng(0).permutation(B)
+    _, rp = run(perm)
+    assert np.array_equal(rp["x"], x[perm])
