@@ -230,7 +230,10 @@ def main():
     dua = np.abs(np.einsum("bij,bj->bi", host["H"], x) + host["g"] + np.einsum("bji,bj->bi", host["A"], chk["y"]) + np.einsum("bji,bj->bi", host["C"], chk["z"])).max()
     assert pri <= 1e-9 and dua <= 1e-9, (pri, dua)
 
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: kernels, memsets and the timing events
+    # all go to THIS stream (handle 0 would select the batch's own stream)
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
 
     def sync_all():
         torch.cuda.synchronize()

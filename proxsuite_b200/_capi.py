@@ -96,6 +96,7 @@ def lib():
     L.pqp_batch_timings.argtypes = [vp, vp, vp, vp]
     L.pqp_batch_debug_trace.argtypes = [vp, vp, i64]
     L.pqp_batch_launch_config.argtypes = [vp, vp, vp, vp, vp]
+    L.pqp_batch_profile.argtypes = [vp, vp, C.c_int]
     L.pqp_random_qp.argtypes = [C.c_int, C.c_uint64, i64, i64, i64, dbl, dbl] + [vp] * 9
     _lib = L
     return L

@@ -66,6 +66,7 @@ struct pqp_batch
   double* ws = nullptr;
   double* dbg = nullptr;
   int dbg_cap = 0;
+  long long* prof = nullptr;
   int64_t launches = 0;
   bool solve_pending = false;
 };
@@ -143,11 +144,12 @@ make_layout(pqp_batch* b)
   vsz[V_HDX] = n; vsz[V_ADX] = ne; vsz[V_ATDY] = n; vsz[V_CDX] = nc; vsz[V_CTDZ] = n; vsz[V_Q] = n;
   vsz[V_GS] = n; vsz[V_BS] = ne; vsz[V_US] = nc; vsz[V_LS] = nc; vsz[V_IS] = n; vsz[V_DELTA] = n + ne + nc;
   vsz[V_B] = ne; vsz[V_U] = nc; vsz[V_L] = nc;
-  vsz[V_D1INV] = n; vsz[V_DSV] = cap; vsz[V_DSINV] = cap;
+  vsz[V_D1INV] = n; vsz[V_DSV] = 2; vsz[V_DSINV] = 2;
   vsz[V_T1] = n; vsz[V_T2] = n; vsz[V_T3] = n;
   vsz[V_S1] = cap + 1; vsz[V_S2] = cap + 1; vsz[V_S3] = cap + 1; vsz[V_S4] = cap + 1;
   vsz[V_ALPHAS] = 2 * nc + 2; vsz[V_GRADS] = 4;
-  vsz[V_SCRATCH] = PQP_NT; vsz[V_RED] = 128;
+  // partial sums: R x ncol (<= NT) for the column-parallel primitives, NW x n for mat_pass
+  vsz[V_SCRATCH] = std::max<int>(PQP_NW * (n <= 128 && cap <= 128 ? 128 : (n <= 160 && cap <= 160 ? 160 : 256)), (n <= 256 && (n % 2) == 0) ? PQP_NW * n : 0); vsz[V_RED] = PQP_NW * 16; // block_reduce: up to 10 values per warp
   int off = 0;
   for (int v = 0; v < V_COUNT; ++v) {
     L.voff[v] = off;
@@ -156,9 +158,9 @@ make_layout(pqp_batch* b)
   L.vec_doubles = off;
   L.scratch_doubles = PQP_NT;
   int64_t sz[PA_COUNT];
-  sz[PA_M1] = (d.hess == PQP_HESSIAN_DENSE) ? rnd((int64_t)n * (n - 1) / 2) : 2;
+  sz[PA_M1] = (d.hess == PQP_HESSIAN_DENSE) ? rnd((int64_t)n * (n + 1) / 2) : 2; // P^-1, packed with diagonal
   sz[PA_AS] = rnd((int64_t)ne * n);
-  sz[PA_MS] = rnd((int64_t)cap * (cap - 1) / 2 + 2);
+  sz[PA_MS] = rnd((int64_t)cap * (cap + 1) / 2 + 2);                                // S^-1, packed with diagonal
   sz[PA_G] = rnd((int64_t)cap * (cap + 1) / 2 + 2);
   sz[PA_Y] = 2;
   sz[PA_VEC] = L.vec_doubles;
@@ -561,6 +563,7 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
       return nullptr;
     }
   }
+  if (std::getenv("PQP_PROFILE")) dev_alloc(b, &b->prof, 16);
   if (std::getenv("PQP_DEBUG_TRACE")) {
     b->dbg_cap = 6 * 4096;
     dev_alloc(b, &b->dbg, (size_t)b->dbg_cap);
@@ -751,6 +754,7 @@ pqp_batch_solve_async(pqp_batch* b, void* stream_)
   a.dbg = b->dbg;
   a.dbg_cap = b->dbg_cap;
   a.dbg_qp = 0;
+  a.prof = b->prof;
   if (const char* e = std::getenv("PQP_DEBUG_TRACE")) a.dbg_qp = std::atoi(e);
   if (const char* e = std::getenv("PQP_WATCHDOG_MS")) a.watchdog_ns = 1000000ull * (unsigned long long)std::atoll(e);
   CUDA_TRY(cudaEventRecord(b->ev2, st));
@@ -909,6 +913,17 @@ pqp_batch_timings(const pqp_batch* b, double* setup_ms, double* solve_ms, int64_
   }
   if (launches) *launches = b->launches;
   return 0;
+}
+
+// per-phase cycle counters accumulated since creation (PQP_PROFILE=1 in the environment)
+int
+pqp_batch_profile(pqp_batch* b, long long* out12, int reset)
+{
+  if (!b || !b->prof) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out12, b->prof, sizeof(long long) * 12, cudaMemcpyDeviceToHost);
+  if (reset) cudaMemset(b->prof, 0, sizeof(long long) * 16);
+  return 12;
 }
 
 // debug trace access (PQP_DEBUG_TRACE=<qp index> in the environment)

@@ -15,7 +15,9 @@
 #include "../../include/pqp.h"
 #include <stdint.h>
 
-#define PQP_NT 256          // threads per CTA (8 warps = one warp-group pair per QP)
+#ifndef PQP_NT
+#define PQP_NT 512          // threads per CTA (16 warps = four warp-groups own one QP)
+#endif
 #define PQP_NW (PQP_NT / 32)
 #define PQP_INFO_DOUBLES 20
 
@@ -58,9 +60,9 @@ struct PqpBatchPtrs
 // Arrays the solve kernel places either in shared memory or in the per-CTA
 // global workspace (decided on the host, see pqp_layout.cpp).
 enum PqpArr {
-  PA_M1 = 0,   // strict lower packed inverse factor of P = Hs + rho I : n(n-1)/2
+  PA_M1 = 0,   // P^-1 = (Hs + rho I)^-1, packed lower with diagonal : n(n+1)/2
   PA_AS,       // scaled equality matrix ne x n
-  PA_MS,       // strict lower packed inverse factor of the dual Schur block : cap(cap-1)/2
+  PA_MS,       // S^-1 (inverse of the dual Schur complement), packed lower with diagonal : cap(cap+1)/2
   PA_G,        // packed lower (with diagonal) Gram matrix B P^-1 B^T by row id : cap(cap+1)/2
   PA_Y,        // n x max(ne, 1) temporary (P^-1 A^T)
   PA_VEC,      // all vectors, one arena (sub-offsets below)
@@ -109,6 +111,7 @@ struct PqpSolveArgs
   double* dbg;       // optional debug trace buffer (NULL = off)
   int32_t dbg_qp;
   int32_t dbg_cap;
+  long long* prof;   // optional per-phase cycle counters (12 entries), NULL = off
   unsigned long long watchdog_ns; // 0 = off; per-QP time budget after which the QP is abandoned (status MAX_ITER_REACHED)
 };
 

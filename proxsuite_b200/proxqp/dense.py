@@ -480,6 +480,15 @@ class DenseBatch:
         G.lib.pqp_batch_launch_config(G.handle, ct.cast(ct.pointer(grid), _VP), ct.cast(ct.pointer(smem), _VP), ct.cast(ct.pointer(mask), _VP), ct.cast(ct.pointer(ws), _VP))
         return dict(grid=grid.value, smem_bytes=smem.value, in_smem_mask=mask.value, ws_doubles=ws.value)
 
+    PROFILE_PHASES = ["stage", "build_M1", "eq_block", "insert", "delete", "solve_kkt", "kkt_residual", "linesearch",
+                      "mu_update", "global_residuals", "newton_misc", "total"]
+
+    def profile(self, reset=True):
+        """Per-phase SM cycles summed over all QPs solved so far (PQP_PROFILE=1)."""
+        out = (ct.c_longlong * 12)()
+        k = self._g.lib.pqp_batch_profile(self._g.handle, out, int(reset))
+        return {n: int(out[i]) for i, n in enumerate(self.PROFILE_PHASES)} if k else None
+
     def debug_trace(self):
         out = np.zeros(6 * 4096)
         k = self._g.lib.pqp_batch_debug_trace(self._g.handle, _ptr(out), out.size)

@@ -107,6 +107,13 @@ if __name__ == "__main__":
             run_case("box_small", "box_benchmark", 8, 15, 5, 5, box=True, sparsity=0.5)
             run_case("degenerate", "degenerate", 8, 20, 5, 5)
             run_case("not_strongly_convex", "not_strongly_convex", 8, 20, 10, 10)
+        if which == "prof":
+            db, data, res = run_case("cfg2_prof", "strongly_convex", 1024, 100, 50, 100, compare=False, reps=1)
+            pr = db.profile()
+            tot = pr["total"]
+            out["profile_cycles_per_qp"] = {k: v / 1024 for k, v in pr.items()}
+            print("cycles per QP:", {k: round(v / 1024) for k, v in pr.items()})
+            print("share:", {k: round(v / tot, 3) for k, v in pr.items()})
         if which in ("all", "perf"):
             run_case("cfg2_1024", "strongly_convex", 1024, 100, 50, 100, compare=False, reps=3)
     finally:
