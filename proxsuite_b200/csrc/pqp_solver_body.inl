@@ -27,6 +27,7 @@ struct Ctx
   int *iscratch; // 2*NW + 8 ints
   double c_scale; // ruiz.c
   long long* prof; // per-phase cycle counters (shared memory) or NULL
+  int vec_smem;    // 1: the vector arena is in shared memory
 };
 
 // local (register) copies of the vector pointers with the address-space hint
@@ -454,98 +455,83 @@ __device__ __forceinline__ const double* get_row(const Ctx& c, const RowSrc& rs,
 // Fused streaming pass over a set of rows (the HBM/L2-facing primitive):
 //   out_dot[idx(r)]  = row_r . x                                       (if x != null)
 //   out_axpy[j]      = add[j] + sign * sum_r coef[idx(r)] row_r[j]     (if coef != null)
-// Each warp keeps U rows in flight so that a pass has 8 warps x U rows x CPL
-// loads outstanding; every matrix element is loaded once and used for both
-// products. VEC = 2: 16-byte loads (even n), VEC = 1: any n.
-template<int CPL, int VEC, int U>
-__device__ void mat_pass_t(const Ctx& c, RowSrc rs, int r0, int r1, const double* __restrict__ x, double* __restrict__ out_dot, const double* __restrict__ coef, double* out_axpy, const double* add, double sign)
+// Warp w owns rows r0 + w + NW*k and handles them four at a time: the eight
+// 16-byte loads of a group are issued together, the four row sums share one
+// transpose-reduction, and every matrix element is loaded once for both
+// products. n must be even and <= 128 (two double2 per lane).
+template<int MODE>
+__device__ void mat_pass_fast(const Ctx& c, RowSrc rs, int r0, int r1, const double* __restrict__ x, double* __restrict__ out_dot, const double* __restrict__ coef, double* out_axpy, const double* add, double sign)
 {
-  PQP_VECS(c);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = c.n;
-  const int nv = (VEC == 2) ? (n >> 1) : n; // row length in load units
+  const int n = c.n, n2 = c.n >> 1;
   const bool DOT = x != nullptr, AXPY = coef != nullptr;
-  double xr[CPL][VEC], acc[CPL][VEC];
-#pragma unroll
-  for (int k = 0; k < CPL; ++k) {
-    const int jv = lane + 32 * k;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      xr[k][e] = (DOT && jv < nv) ? x[jv * VEC + e] : 0.0;
-      acc[k][e] = 0.0;
-    }
+  double* const scr = c.scratch;
+  const double* const isv = c.is;
+  PQP_SM(scr);
+  PQP_SM(isv);
+  if (DOT) {
+    PQP_SM(x);
+    PQP_SM(out_dot);
   }
-  for (int rb = r0 + warp; rb < r1; rb += NW * U) {
-    const double* rowp[U];
-    int bk[U], idx[U];
-    bool ok[U];
-    double v[U][CPL][VEC];
+  if (AXPY) {
+    PQP_SM(coef);
+    PQP_SM(out_axpy);
+  }
+  const bool l1 = lane + 32 < n2; // second double2 of the row belongs to this lane
+  double2 x0 = make_double2(0.0, 0.0), x1 = x0, acc0 = x0, acc1 = x0;
+  if (DOT) {
+    if (lane < n2) x0 = reinterpret_cast<const double2*>(x)[lane];
+    if (l1) x1 = reinterpret_cast<const double2*>(x)[lane + 32];
+  }
+  RowSrc one = rs;
+  one.mode = MODE;
+  for (int rb = r0 + warp; rb < r1; rb += 4 * NW) {
+    const double* rowp[4];
+    int bk[4], idx[4];
+    double2 v0[4], v1[4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int r = rb + u * NW;
-      ok[u] = r < r1;
       rowp[u] = nullptr;
       bk[u] = -1;
-      idx[u] = 0;
-      if (ok[u]) rowp[u] = get_row(c, rs, r, bk[u], idx[u]);
+      idx[u] = -1;
+      if (r < r1) rowp[u] = get_row(c, one, r, bk[u], idx[u]);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        const int jv = lane + 32 * k;
-        if (VEC == 2) {
-          double2 t = (rowp[u] && jv < nv) ? reinterpret_cast<const double2*>(rowp[u])[jv] : make_double2(0.0, 0.0);
-          v[u][k][0] = t.x;
-          v[u][k][VEC - 1] = t.y;
-        } else {
-          v[u][k][0] = (rowp[u] && jv < nv) ? rowp[u][jv] : 0.0;
-        }
-      }
+    for (int u = 0; u < 4; ++u) {
+      v0[u] = (rowp[u] && lane < n2) ? reinterpret_cast<const double2*>(rowp[u])[lane] : make_double2(0.0, 0.0);
+      v1[u] = (rowp[u] && l1) ? reinterpret_cast<const double2*>(rowp[u])[lane + 32] : make_double2(0.0, 0.0);
     }
     if (DOT) {
-      double d[U];
+      double d[4];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        double a = 0;
-#pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) a += v[u][k][e] * xr[k][e];
-        }
-        d[u] = a;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) d[u] += __shfl_xor_sync(FULL, d[u], o);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (ok[u]) out_dot[idx[u]] = rowp[u] ? d[u] : v_is[bk[u]] * x[bk[u]];
-        }
+      for (int u = 0; u < 4; ++u) d[u] = (v0[u].x * x0.x + v0[u].y * x0.y) + (v1[u].x * x1.x + v1[u].y * x1.y);
+      reduce_rows<4>(d, lane);
+      if ((lane & 7) == 0) {
+        const int u = lane >> 3;
+        // (rowp / idx are warp-uniform per u; select without dynamic indexing)
+        const int id = (u == 0) ? idx[0] : (u == 1) ? idx[1] : (u == 2) ? idx[2] : idx[3];
+        const int bb = (u == 0) ? bk[0] : (u == 1) ? bk[1] : (u == 2) ? bk[2] : bk[3];
+        if (id >= 0) out_dot[id] = (bb < 0) ? d[0] : isv[bb] * x[bb];
       }
     }
     if (AXPY) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!ok[u]) continue;
-        const double cf = coef[idx[u]];
-        if (rowp[u]) {
-#pragma unroll
-          for (int k = 0; k < CPL; ++k) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[k][e] += cf * v[u][k][e];
-          }
-        } else {
-          const int jv = bk[u] / VEC, je = bk[u] % VEC;
-          const double add_v = cf * v_is[bk[u]];
-#pragma unroll
-          for (int k = 0; k < CPL; ++k) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-              if (jv == lane + 32 * k && je == e) acc[k][e] += add_v;
+      for (int u = 0; u < 4; ++u) {
+        if (idx[u] >= 0) {
+          const double cf = coef[idx[u]];
+          if (bk[u] < 0) {
+            acc0.x += cf * v0[u].x;
+            acc0.y += cf * v0[u].y;
+            acc1.x += cf * v1[u].x;
+            acc1.y += cf * v1[u].y;
+          } else {
+            const int jv = bk[u] >> 1;
+            const double add_v = cf * isv[bk[u]];
+            if (jv == lane) {
+              if (bk[u] & 1) acc0.y += add_v; else acc0.x += add_v;
+            } else if (jv == lane + 32) {
+              if (bk[u] & 1) acc1.y += add_v; else acc1.x += add_v;
             }
           }
         }
@@ -553,19 +539,13 @@ __device__ void mat_pass_t(const Ctx& c, RowSrc rs, int r0, int r1, const double
     }
   }
   if (AXPY) {
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-      const int jv = lane + 32 * k;
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        if (jv < nv) v_scratch[warp * n + jv * VEC + e] = acc[k][e];
-      }
-    }
+    if (lane < n2) reinterpret_cast<double2*>(scr)[warp * n2 + lane] = acc0;
+    if (l1) reinterpret_cast<double2*>(scr)[warp * n2 + lane + 32] = acc1;
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += NT) {
       double sacc = 0;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) sacc += v_scratch[w * n + j];
+      for (int w = 0; w < NW; ++w) sacc += scr[w * n + j];
       out_axpy[j] = (add ? add[j] : 0.0) + sign * sacc;
     }
   }
@@ -615,12 +595,13 @@ __device__ void rows_axpy_t(const Ctx& c, RowSrc rs, int r0, int r1, const doubl
 __device__ __noinline__ void mat_pass(const Ctx& c, RowSrc rs, int r0, int r1, const double* x, double* out_dot, const double* coef, double* out_axpy, const double* add, double sign)
 {
   const int n = c.n;
-  if ((n & 1) == 0 && n <= 128) {
-    mat_pass_t<2, 2, 8>(c, rs, r0, r1, x, out_dot, coef, out_axpy, add, sign);
-  } else if (n <= 128) {
-    mat_pass_t<4, 1, 4>(c, rs, r0, r1, x, out_dot, coef, out_axpy, add, sign);
-  } else if ((n & 1) == 0 && n <= 256) {
-    mat_pass_t<4, 2, 4>(c, rs, r0, r1, x, out_dot, coef, out_axpy, add, sign);
+  if ((n & 1) == 0 && n <= 128 && c.vec_smem) {
+    switch (rs.mode) {
+      case 0: mat_pass_fast<0>(c, rs, r0, r1, x, out_dot, coef, out_axpy, add, sign); break;
+      case 1: mat_pass_fast<1>(c, rs, r0, r1, x, out_dot, coef, out_axpy, add, sign); break;
+      case 2: mat_pass_fast<2>(c, rs, r0, r1, x, out_dot, coef, out_axpy, add, sign); break;
+      default: mat_pass_fast<3>(c, rs, r0, r1, x, out_dot, coef, out_axpy, add, sign); break;
+    }
   } else {
     if (x) rows_dot(c, rs, r0, r1, x, out_dot);
     if (coef) rows_axpy_t(c, rs, r0, r1, coef, out_axpy, add, sign);
@@ -1842,6 +1823,7 @@ __global__ void __launch_bounds__(NT, 1) pqp_solve_kernel(PqpSolveArgs A)
   if (threadIdx.x == 0) {
     for (int k = 0; k < PH_COUNT; ++k) prof_sh[k] = 0;
     c.prof = A.prof ? prof_sh : nullptr;
+    c.vec_smem = L.in_smem[PA_VEC];
     double* ws = A.ws + (size_t)blockIdx.x * (size_t)L.ws_doubles;
     auto place = [&](int id) -> double* { return (L.in_smem[id] ? smem_dyn : ws) + L.off[id]; };
     c.n = A.d.n;
