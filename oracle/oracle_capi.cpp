@@ -188,6 +188,12 @@ orc_qp_counters(void* p, double* out, int reset)
   if (reset) c = Counters();
 }
 
+long long
+orc_qp_max_nc(void* p)
+{
+  return static_cast<QP*>(p)->work.max_nc;
+}
+
 // ---- batch (std::vector<QP> / BatchQP, wrapper.hpp:1253-1311) --------------
 void*
 orc_batch_create(long long batch, long long n, long long n_eq, long long n_in, int box, int hessian, int backend)

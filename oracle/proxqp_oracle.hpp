@@ -407,6 +407,7 @@ struct Workspace
   std::vector<isize> ibuf;
   bool constraints_changed = false, dirty = false, refactorize = false, proximal_parameter_update = false, is_initialized = false;
   isize n_c = 0;
+  isize max_nc = 0; // largest active-set size seen (statistics only)
   Counters cnt;
 
   Workspace() = default;

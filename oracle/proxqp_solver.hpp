@@ -903,6 +903,7 @@ active_set_change(QP& qp)
     }
   }
   w.n_c = n_c_f;
+  if (n_c_f > w.max_nc) w.max_nc = n_c_f;
   w.current_bijection_map = w.new_bijection_map;
 }
 
