@@ -60,14 +60,16 @@ struct pqp_batch
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   bool setup_timed = false, solve_timed = false;
-  PqpLayout lay{};
-  int grid = 0;
+  PqpLayout lay{};      // primary layout (fast kernel when the inverse blocks are in shared memory)
+  PqpLayout lay_gen{};  // fallback: everything but the vectors in global memory, full capacity
+  int grid = 0, grid_gen = 0;
   int32_t* counter = nullptr;
   double* ws = nullptr;
   double* dbg = nullptr;
   int dbg_cap = 0;
   long long* prof = nullptr;
   int64_t launches = 0;
+  int64_t overflow_retries = 0;
   bool solve_pending = false;
 };
 
@@ -124,17 +126,23 @@ cold_start(pqp_info& i, const pqp_settings* s, int backend)
   cleanup_statistics(i);
 }
 
-// Shared-memory placement policy. Everything that does not fit the budget
-// lives in the per-CTA global workspace (L2-resident).
+// Shared-memory placement policy. Three layouts, all served by the same device
+// code (arrays are addressed through per-array pointers):
+//   compact : vectors + S^-1 (capacity si_cap) in shared memory, P^-1 / A_s / G
+//             in the per-CTA global workspace (L2-resident) -> TWO CTAs per SM.
+//             The solver is latency bound, so a second
+//             resident QP per SM nearly doubles throughput.
+//   full    : vectors, P^-1, S^-1 (full capacity) and A_s in shared memory,
+//             one CTA per SM.
+//   generic : only the vectors in shared memory; used for shapes that fit
+//             neither, and to re-solve the rare QPs whose active set outgrows
+//             si_cap in the compact layout.
 int
-make_layout(pqp_batch* b)
+fill_layout(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, bool want_m1, bool want_ms, bool want_as, int si_cap, int ctas)
 {
-  const PqpDims& d = b->d;
-  PqpLayout& L = b->lay;
   std::memset(&L, 0, sizeof(L));
   const int n = d.n, ne = d.ne, nc = d.nc, cap = d.cap;
   auto rnd = [](int64_t v) { return (v + 1) & ~int64_t(1); };
-  // vector arena
   int vsz[V_COUNT];
   for (int& v : vsz) v = 0;
   vsz[V_X] = n; vsz[V_Y] = ne; vsz[V_Z] = nc; vsz[V_XP] = n; vsz[V_YP] = ne; vsz[V_ZP] = nc;
@@ -148,31 +156,29 @@ make_layout(pqp_batch* b)
   vsz[V_T1] = n; vsz[V_T2] = n; vsz[V_T3] = n;
   vsz[V_S1] = cap + 1; vsz[V_S2] = cap + 1; vsz[V_S3] = cap + 1; vsz[V_S4] = cap + 1;
   vsz[V_ALPHAS] = 2 * nc + 2; vsz[V_GRADS] = 4;
-  // partial sums: R x ncol (<= NT) for the column-parallel primitives, NW x n for mat_pass
-  vsz[V_SCRATCH] = std::max<int>(PQP_NW * (n <= 128 && cap <= 128 ? 128 : (n <= 160 && cap <= 160 ? 160 : 256)), (n <= 256 && (n % 2) == 0) ? PQP_NW * n : 0); vsz[V_RED] = PQP_NW * 16; // block_reduce: up to 10 values per warp
+  // partial sums: NW x 32*NG for the symmetric mat-vec, NW x n for the row passes
+  const int ncols = (n <= 128 && cap <= 128) ? 128 : ((n <= 160 && cap <= 160) ? 160 : 256);
+  vsz[V_SCRATCH] = std::max<int>(PQP_NW * ncols, (n <= 256 && (n % 2) == 0) ? PQP_NW * n : PQP_NT);
+  vsz[V_RED] = PQP_NW * 16; // block_reduce: up to 10 values per warp
   int off = 0;
   for (int v = 0; v < V_COUNT; ++v) {
     L.voff[v] = off;
     off += (int)rnd(vsz[v]);
   }
   L.vec_doubles = off;
-  L.scratch_doubles = PQP_NT;
+  L.scratch_doubles = vsz[V_SCRATCH];
+  L.si_cap = si_cap;
+  L.ctas_per_sm = ctas;
   int64_t sz[PA_COUNT];
   sz[PA_M1] = (d.hess == PQP_HESSIAN_DENSE) ? rnd((int64_t)n * (n + 1) / 2) : 2; // P^-1, packed with diagonal
   sz[PA_AS] = rnd((int64_t)ne * n);
-  sz[PA_MS] = rnd((int64_t)cap * (cap + 1) / 2 + 2);                                // S^-1, packed with diagonal
+  sz[PA_MS] = rnd((int64_t)si_cap * (si_cap + 1) / 2 + 2);                       // S^-1, packed with diagonal
   sz[PA_G] = rnd((int64_t)cap * (cap + 1) / 2 + 2);
   sz[PA_Y] = 2;
   sz[PA_VEC] = L.vec_doubles;
   const int64_t nlist = std::max(nc, cap);
   L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);
-  int max_smem = pqp_solve_max_smem();
-  if (max_smem <= 0) return fail(PQP_ECUDA, "no CUDA device / cannot query shared memory");
-  int64_t budget = (int64_t)max_smem - 1024 /*static*/ - L.smem_int_bytes;
-  if (const char* e = std::getenv("PQP_SMEM_BUDGET")) {
-    int64_t v = std::atoll(e);
-    if (v > 0) budget = std::min(budget, v - 1024 - (int64_t)L.smem_int_bytes);
-  }
+  const int64_t budget = budget_bytes - 1024 /*static shared memory*/ - L.smem_int_bytes;
   int64_t smem_d = 0, ws_d = 0;
   auto put = [&](int id, bool want_smem) {
     if (want_smem && (smem_d + sz[id]) * 8 <= budget) {
@@ -186,13 +192,71 @@ make_layout(pqp_batch* b)
     }
   };
   put(PA_VEC, true);
-  put(PA_M1, true);
-  put(PA_MS, true);
-  put(PA_AS, true);
+  put(PA_MS, want_ms);
+  put(PA_M1, want_m1);
+  put(PA_AS, want_as);
   put(PA_G, false);
   put(PA_Y, false);
   L.smem_doubles = (int32_t)smem_d;
   L.ws_doubles = std::max<int64_t>(ws_d, 2);
+  return 0;
+}
+
+int64_t
+sym_doubles(int64_t m)
+{
+  return m * (m + 1) / 2 + 2;
+}
+
+int
+make_layout(pqp_batch* b)
+{
+  const PqpDims& d = b->d;
+  int max_smem = pqp_solve_max_smem();
+  if (max_smem <= 0) return fail(PQP_ECUDA, "no CUDA device / cannot query shared memory");
+  int smem_sm = 0;
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, b->device);
+  if (smem_sm <= 0) smem_sm = max_smem + 1024;
+  const char* mode = std::getenv("PQP_LAYOUT"); // "compact" | "full" | "generic" | unset (auto)
+  const std::string m = mode ? mode : "auto";
+  // generic fallback first (always valid as long as the vectors fit somewhere)
+  fill_layout(d, b->lay_gen, max_smem, false, false, false, d.cap, 1);
+  bool done = false;
+  if (m == "auto" || m == "compact") {
+    // two CTAs per SM: each gets half of the SM's shared memory minus the 1 KB system reserve
+    const int64_t per_cta = ((int64_t)smem_sm - 2 * 1024) / 2;
+    PqpLayout probe;
+    fill_layout(d, probe, per_cta, false, false, false, 1, 2); // vectors only, to measure them
+    const int64_t left = (per_cta - 1024 - probe.smem_int_bytes) / 8 - probe.vec_doubles;
+    int cap2 = 0;
+    for (int cnd = d.cap; cnd >= 1; --cnd) {
+      if (sym_doubles(cnd) + 2 <= left) {
+        cap2 = cnd;
+        break;
+      }
+    }
+    bool forced_cap = false;
+    if (const char* e = std::getenv("PQP_SI_CAP")) { // test hook: force a small capacity to exercise the retry path
+      int v = std::atoi(e);
+      if (v >= d.ne + 1 && v < cap2) {
+        cap2 = v;
+        forced_cap = true;
+      }
+    }
+    // worth it only if the shared-memory S^-1 holds the equalities plus a healthy share of the
+    // inequalities, and P^-1 can be swept inside that region
+    const int need = d.ne + std::min(d.nc, std::max(8, (3 * d.nc + 3) / 4));
+    const bool pi_ok = d.hess != PQP_HESSIAN_DENSE || sym_doubles(d.n) <= sym_doubles(cap2);
+    if (probe.in_smem[PA_VEC] && (cap2 >= std::min(d.cap, need) || forced_cap) && pi_ok) {
+      fill_layout(d, b->lay, per_cta, false, true, false, cap2, 2);
+      done = b->lay.in_smem[PA_MS] != 0;
+    }
+  }
+  if (!done && (m == "auto" || m == "full" || m == "compact")) {
+    fill_layout(d, b->lay, max_smem, true, true, true, d.cap, 1);
+    done = b->lay.in_smem[PA_VEC] && b->lay.in_smem[PA_MS] && b->lay.in_smem[PA_M1];
+  }
+  if (!done) b->lay = b->lay_gen;
   return 0;
 }
 
@@ -363,6 +427,32 @@ void
 fill_vec(std::vector<double>& v, double val)
 {
   std::fill(v.begin(), v.end(), val);
+}
+
+// upload the per-QP launch parameters and enqueue one persistent solve kernel
+int
+enqueue_solve(pqp_batch* b, cudaStream_t st, const PqpLayout& lay, int grid)
+{
+  CUDA_TRY(cudaMemcpyAsync(b->p.params, b->hparams.data(), sizeof(PqpQpParams) * (size_t)b->B, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(b->counter, 0, sizeof(int32_t), st));
+  PqpSolveArgs a{};
+  a.d = b->d;
+  a.p = b->p;
+  a.lay = lay;
+  a.batch = (int32_t)b->B;
+  a.counter = b->counter;
+  a.ws = b->ws;
+  a.dbg = b->dbg;
+  a.dbg_cap = b->dbg_cap;
+  a.dbg_qp = 0;
+  a.prof = b->prof;
+  if (const char* e = std::getenv("PQP_DEBUG_TRACE")) a.dbg_qp = std::atoi(e);
+  if (const char* e = std::getenv("PQP_WATCHDOG_MS")) a.watchdog_ns = 1000000ull * (unsigned long long)std::atoll(e);
+  CUDA_TRY(cudaEventRecord(b->ev2, st));
+  int rc = pqp_launch_solve(&a, grid, st);
+  if (rc != 0) return fail(PQP_ECUDA, std::string("solve kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+  CUDA_TRY(cudaEventRecord(b->ev3, st));
+  return 0;
 }
 
 } // namespace
@@ -546,19 +636,21 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
     pqp_batch_destroy(b);
     return nullptr;
   }
-  // persistent grid: resident CTAs per SM x SM count, never more than the batch
+  // persistent grids: resident CTAs per SM x SM count, never more than the batch
   {
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    size_t smem = sizeof(double) * (size_t)b->lay.smem_doubles + (size_t)b->lay.smem_int_bytes;
-    int max_smem_sm = 0;
-    cudaDeviceGetAttribute(&max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
-    int per_sm = (int)std::max<size_t>(1, (size_t)max_smem_sm / (smem + 2048));
-    per_sm = std::min(per_sm, 2048 / PQP_NT);
-    if (const char* e = std::getenv("PQP_CTAS_PER_SM")) per_sm = std::max(1, std::atoi(e));
-    int64_t g = (int64_t)sms * per_sm;
-    b->grid = (int)std::max<int64_t>(1, std::min<int64_t>(g, std::max<int64_t>(batch, 1)));
-    if (dev_alloc(b, &b->ws, (size_t)b->grid * (size_t)b->lay.ws_doubles) != 0) {
+    auto grid_for = [&](const PqpLayout& L) {
+      int per_sm = std::max(1, (int)L.ctas_per_sm);
+      per_sm = std::min(per_sm, 2048 / PQP_NT);
+      if (const char* e = std::getenv("PQP_CTAS_PER_SM")) per_sm = std::max(1, std::atoi(e));
+      int64_t g = (int64_t)sms * per_sm;
+      return (int)std::max<int64_t>(1, std::min<int64_t>(g, std::max<int64_t>(batch, 1)));
+    };
+    b->grid = grid_for(b->lay);
+    b->grid_gen = grid_for(b->lay_gen);
+    const size_t ws = std::max((size_t)b->grid * (size_t)b->lay.ws_doubles, (size_t)b->grid_gen * (size_t)b->lay_gen.ws_doubles);
+    if (dev_alloc(b, &b->ws, ws) != 0) {
       pqp_batch_destroy(b);
       return nullptr;
     }
@@ -742,25 +834,7 @@ pqp_batch_solve_async(pqp_batch* b, void* stream_)
     p.mu_eq = info.mu_eq;
     p.mu_in = info.mu_in;
   }
-  CUDA_TRY(cudaMemcpyAsync(b->p.params, b->hparams.data(), sizeof(PqpQpParams) * (size_t)b->B, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemsetAsync(b->counter, 0, sizeof(int32_t), st));
-  PqpSolveArgs a{};
-  a.d = b->d;
-  a.p = b->p;
-  a.lay = b->lay;
-  a.batch = (int32_t)b->B;
-  a.counter = b->counter;
-  a.ws = b->ws;
-  a.dbg = b->dbg;
-  a.dbg_cap = b->dbg_cap;
-  a.dbg_qp = 0;
-  a.prof = b->prof;
-  if (const char* e = std::getenv("PQP_DEBUG_TRACE")) a.dbg_qp = std::atoi(e);
-  if (const char* e = std::getenv("PQP_WATCHDOG_MS")) a.watchdog_ns = 1000000ull * (unsigned long long)std::atoll(e);
-  CUDA_TRY(cudaEventRecord(b->ev2, st));
-  int rc = pqp_launch_solve(&a, b->grid, st);
-  if (rc != 0) return fail(PQP_ECUDA, std::string("solve kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
-  CUDA_TRY(cudaEventRecord(b->ev3, st));
+  if (int rc = enqueue_solve(b, st, b->lay, b->grid)) return rc;
   b->solve_timed = true;
   b->launches += 1;
   b->solve_pending = true;
@@ -783,6 +857,30 @@ pqp_batch_sync(pqp_batch* b)
   if (b->solve_pending) {
     std::vector<double> raw((size_t)b->B * PQP_INFO_DOUBLES);
     CUDA_TRY(cudaMemcpy(raw.data(), b->p.info, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost));
+    // QPs whose active set outgrew the shared-memory S^-1 of the compact layout
+    // report the internal status 99: re-solve exactly those with the generic
+    // kernel (full capacity, inverse blocks in global memory).
+    {
+      std::vector<int64_t> retry;
+      for (int64_t i = 0; i < b->B; ++i) {
+        if (b->hparams[i].active && raw[(size_t)i * PQP_INFO_DOUBLES + 10] == 99.0) retry.push_back(i);
+      }
+      if (!retry.empty()) {
+        std::vector<int32_t> saved((size_t)b->B);
+        for (int64_t i = 0; i < b->B; ++i) {
+          saved[i] = b->hparams[i].active;
+          b->hparams[i].active = 0;
+        }
+        for (int64_t i : retry) b->hparams[i].active = 1;
+        int rc = enqueue_solve(b, b->stream, b->lay_gen, b->grid_gen);
+        for (int64_t i = 0; i < b->B; ++i) b->hparams[i].active = saved[i];
+        if (rc != 0) return rc;
+        b->launches += 1;
+        b->overflow_retries += (int64_t)retry.size();
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        CUDA_TRY(cudaMemcpy(raw.data(), b->p.info, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost));
+      }
+    }
     float ms_solve = 0, ms_setup = 0;
     if (b->solve_timed) cudaEventElapsedTime(&ms_solve, b->ev2, b->ev3);
     if (b->setup_timed) cudaEventElapsedTime(&ms_setup, b->ev0, b->ev1);
@@ -946,7 +1044,7 @@ pqp_batch_launch_config(const pqp_batch* b, int* grid, int* smem_bytes, int* in_
     for (int i = 0; i < PA_COUNT; ++i) m |= (b->lay.in_smem[i] ? 1 : 0) << i;
     *in_smem_mask = m;
   }
-  if (ws_doubles) *ws_doubles = b->lay.ws_doubles;
+  if (ws_doubles) *ws_doubles = b->lay.ws_doubles + ((int64_t)b->lay.si_cap << 32) + ((int64_t)b->overflow_retries << 48);
   return 0;
 }
 

@@ -16,7 +16,10 @@
 #include <stdint.h>
 
 #ifndef PQP_NT
-#define PQP_NT 512          // threads per CTA (16 warps = four warp-groups own one QP)
+#define PQP_NT 256          // threads per CTA: two warp-groups own one QP
+#endif
+#ifndef PQP_MIN_CTAS
+#define PQP_MIN_CTAS 2       // resident CTAs per SM the register budget is sized for (compact layout)
 #endif
 #define PQP_NW (PQP_NT / 32)
 #define PQP_INFO_DOUBLES 20
@@ -98,6 +101,8 @@ struct PqpLayout
   int32_t smem_doubles;       // total doubles of dynamic shared memory
   int32_t smem_int_bytes;     // bytes of int scratch that follow the doubles
   int64_t ws_doubles;         // per-CTA global workspace in doubles
+  int32_t si_cap;             // dual-block capacity of the S^-1 storage (<= dims.cap)
+  int32_t ctas_per_sm;        // resident CTAs per SM this layout is sized for
 };
 
 struct PqpSolveArgs

@@ -350,7 +350,9 @@ extern "C" int
 pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream)
 {
   size_t smem = sizeof(double) * (size_t)a->lay.smem_doubles + (size_t)a->lay.smem_int_bytes;
-  const bool fast = a->lay.in_smem[PA_VEC] && a->lay.in_smem[PA_M1] && a->lay.in_smem[PA_MS];
+  // fast kernel: vectors and S^-1 in shared memory; P^-1 either there too or swept inside the S^-1 region
+  const int64_t symn = (int64_t)a->d.n * (a->d.n + 1) / 2, symc = (int64_t)a->lay.si_cap * (a->lay.si_cap + 1) / 2;
+  const bool fast = a->lay.in_smem[PA_VEC] && a->lay.in_smem[PA_MS] && (a->lay.in_smem[PA_M1] || a->d.hess != PQP_HESSIAN_DENSE || symn <= symc);
   auto kern = fast ? fastk::pqp_solve_kernel : genk::pqp_solve_kernel;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

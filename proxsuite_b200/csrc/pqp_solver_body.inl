@@ -28,6 +28,9 @@ struct Ctx
   double c_scale; // ruiz.c
   long long* prof; // per-phase cycle counters (shared memory) or NULL
   int vec_smem;    // 1: the vector arena is in shared memory
+  int pi_smem;     // 1: P^-1 lives in shared memory (else global, read through L2)
+  int si_cap;      // largest dual-block size the S^-1 storage can hold
+  int overflow;    // set when an insertion would exceed si_cap (QP is retried by the generic kernel)
 };
 
 // local (register) copies of the vector pointers with the address-space hint
@@ -228,13 +231,13 @@ __device__ __forceinline__ void reduce_rows(double (&d)[RR], int lane)
 #define RPB (32 / NW) // rows per warp per 32-row block
 
 // y = T x. x and y must not alias. Uses c.scratch (NW x 32*NG doubles).
-template<int NG>
+template<int NG, bool TSM>
 __device__ void sym_mv_fast(const Ctx& c, const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n)
 {
   constexpr int NC = 32 * NG;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* const scr = c.scratch;
-  PQP_SM(T);
+  if (TSM) PQP_SM(T);
   PQP_SM(x);
   PQP_SM(y);
   PQP_SM(scr);
@@ -305,16 +308,25 @@ __device__ void sym_mv_generic(const double* __restrict__ T, const double* __res
   __syncthreads();
 }
 
-__device__ __noinline__ void sym_mv(const Ctx& c, const double* T, const double* x, double* y, int n)
+__device__ __noinline__ void sym_mv(const Ctx& c, const double* T, const double* x, double* y, int n, bool t_smem)
 {
-  if (n <= 128)
-    sym_mv_fast<4>(c, T, x, y, n);
-  else if (n <= 160)
-    sym_mv_fast<5>(c, T, x, y, n);
-  else if (n <= 256)
-    sym_mv_fast<8>(c, T, x, y, n);
-  else
-    sym_mv_generic(T, x, y, n);
+  if (t_smem) {
+    if (n <= 128)
+      sym_mv_fast<4, true>(c, T, x, y, n);
+    else if (n <= 160)
+      sym_mv_fast<5, true>(c, T, x, y, n);
+    else if (n <= 256)
+      sym_mv_fast<8, true>(c, T, x, y, n);
+    else
+      sym_mv_generic(T, x, y, n);
+  } else {
+    if (n <= 128)
+      sym_mv_fast<4, false>(c, T, x, y, n);
+    else if (n <= 256)
+      sym_mv_fast<8, false>(c, T, x, y, n);
+    else
+      sym_mv_generic(T, x, y, n);
+  }
 }
 
 // T[i][j] += u_i * v_j on the packed lower triangle (j <= i < n). If kfix >= 0
@@ -617,7 +629,7 @@ __device__ void apply_Pinv(const Ctx& c, const double* v, double* y)
     __syncthreads();
     return;
   }
-  sym_mv(c, c.Pi, v, y, c.n);
+  sym_mv(c, c.Pi, v, y, c.n, c.pi_smem != 0);
 }
 
 __device__ __forceinline__ int row_id(const Ctx& c, int s)
@@ -644,7 +656,7 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
   mat_pass(c, slots, 0, ns, v_t1, v_s1, nullptr, nullptr, nullptr, 1.0);
   for (int s = threadIdx.x; s < ns; s += NT) v_s1[s] -= b2[s];
   __syncthreads();
-  sym_mv(c, c.Si, v_s1, os, ns);
+  sym_mv(c, c.Si, v_s1, os, ns, true);
   mat_pass(c, slots, 0, ns, nullptr, nullptr, os, v_t2, b1, -1.0);
   apply_Pinv(c, v_t2, ox);
 }
@@ -676,11 +688,16 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu)
 {
   PQP_VECS(c);
   const int s = c.ns;
+  if (s + 1 > c.si_cap) { // does not fit the shared-memory S^-1: hand the QP to the generic kernel
+    if (threadIdx.x == 0) c.overflow = 1;
+    __syncthreads();
+    return;
+  }
   gram_row(c, s);
   __syncthreads();
   double delta = v_s3[s] + mu;
   if (s > 0) {
-    sym_mv(c, c.Si, v_s3, v_s1, s);
+    sym_mv(c, c.Si, v_s3, v_s1, s, true);
     double part = 0;
     for (int j = threadIdx.x; j < s; j += NT) part += v_s3[j] * v_s1[j];
     delta -= block_sum1(c, part);
@@ -793,13 +810,22 @@ __device__ __noinline__ void build_Pi(Ctx& c, double rho)
     return;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // When P^-1 is kept in global memory (compact shared-memory layout, two CTAs
+  // per SM) the sweeps still run in shared memory: the S^-1 region is free at
+  // this point (the dual block is always rebuilt afterwards).
+  double* const work = c.pi_smem ? c.Pi : c.Si;
   for (int i = warp; i < n; i += NW) {
-    double* row = c.Pi + sym_off(i);
+    double* row = work + sym_off(i);
     const double* h = c.Hs + (size_t)i * n;
     for (int j = lane; j <= i; j += 32) row[j] = h[j] + ((j == i) ? rho : 0.0);
   }
   __syncthreads();
-  sym_sweep_invert(c.Pi, v_t1, v_t2, n);
+  sym_sweep_invert(work, v_t1, v_t2, n);
+  if (!c.pi_smem) {
+    const int tot = sym_off(n);
+    for (int e = threadIdx.x; e < tot; e += NT) c.Pi[e] = work[e];
+    __syncthreads();
+  }
 }
 
 // (Re)build the dual block for the slots 0..ns_target-1 currently registered:
@@ -1335,6 +1361,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
     if (tid == 0) {
       c.c_scale = P.c[q];
       c.ns = 0;
+      c.overflow = 0;
     }
     __syncthreads();
   }
@@ -1417,6 +1444,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
     for (int i = tid; i < nc; i += NT) c.act_up[i] = 0;
     __syncthreads();
   }
+  const bool overflow_at_start = c.overflow != 0;
 
   double bcl_eta_ext_init = pow(0.1, S.alpha_bcl);
   double bcl_eta_ext = bcl_eta_ext_init;
@@ -1437,7 +1465,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
   const unsigned long long t_start = A.watchdog_ns ? gtimer_ns() : 0ull;
 
   bool residuals_fresh = false;
-  for (long long iter = 0; iter < S.max_iter; ++iter) {
+  for (long long iter = 0; iter < S.max_iter && !overflow_at_start; ++iter) {
     // The reference recomputes both global residuals here; from the second
     // outer iteration on they were already evaluated for exactly this
     // (x, y, z) at the end of the previous iteration, so the values are reused
@@ -1512,6 +1540,10 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
         }
         __syncthreads();
         active_set_change(c, sc);
+        if (c.overflow) { // S^-1 capacity exceeded: the QP is re-solved by the generic kernel
+          expired = true;
+          break;
+        }
         // q = sum over inactive constraints with z_i != 0 of z_i c_i
         int nq = block_compact(c, nc, c.list2, [&](int i) { return c.cons_slot[i] < 0 && v_z[i] != 0.0; });
         if (nq > 0) {
@@ -1749,6 +1781,12 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
     sc.mu_in_inv = new_mu_in_inv;
   }
 
+  if (c.overflow) {
+    // leave x, y, z untouched (warm starts must see the caller's values again)
+    if (tid == 0) A.p.info[(size_t)q * PQP_INFO_DOUBLES + 10] = 99.0; // internal: retry with the generic kernel
+    __syncthreads();
+    return;
+  }
   // ---- unscale and write back (solver.hpp:1749-1836) -------------------------
   double* xo = A.p.x + (size_t)q * n;
   double* yo = A.p.y + (size_t)q * ne;
@@ -1814,7 +1852,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
 
 extern __shared__ __align__(16) double smem_dyn[];
 
-__global__ void __launch_bounds__(NT, 1) pqp_solve_kernel(PqpSolveArgs A)
+__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArgs A)
 {
   __shared__ Ctx c;
   __shared__ int cur_q;
@@ -1824,6 +1862,9 @@ __global__ void __launch_bounds__(NT, 1) pqp_solve_kernel(PqpSolveArgs A)
     for (int k = 0; k < PH_COUNT; ++k) prof_sh[k] = 0;
     c.prof = A.prof ? prof_sh : nullptr;
     c.vec_smem = L.in_smem[PA_VEC];
+    c.pi_smem = L.in_smem[PA_M1];
+    c.si_cap = L.si_cap;
+    c.overflow = 0;
     double* ws = A.ws + (size_t)blockIdx.x * (size_t)L.ws_doubles;
     auto place = [&](int id) -> double* { return (L.in_smem[id] ? smem_dyn : ws) + L.off[id]; };
     c.n = A.d.n;

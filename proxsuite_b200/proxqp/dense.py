@@ -478,7 +478,8 @@ class DenseBatch:
         grid, smem, mask, ws = ct.c_int(0), ct.c_int(0), ct.c_int(0), ct.c_int64(0)
         G = self._g
         G.lib.pqp_batch_launch_config(G.handle, ct.cast(ct.pointer(grid), _VP), ct.cast(ct.pointer(smem), _VP), ct.cast(ct.pointer(mask), _VP), ct.cast(ct.pointer(ws), _VP))
-        return dict(grid=grid.value, smem_bytes=smem.value, in_smem_mask=mask.value, ws_doubles=ws.value)
+        return dict(grid=grid.value, smem_bytes=smem.value, in_smem_mask=mask.value, ws_doubles=ws.value & 0xffffffff,
+                    si_cap=(ws.value >> 32) & 0xffff, overflow_retries=ws.value >> 48)
 
     PROFILE_PHASES = ["stage", "build_M1", "eq_block", "insert", "delete", "solve_kkt", "kkt_residual", "linesearch",
                       "mu_update", "global_residuals", "newton_misc", "total"]

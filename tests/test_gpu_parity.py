@@ -298,3 +298,33 @@ def test_full_size_batch_properties(px):
     perm = np.random.default_rng(0).permutation(B)
     _, rp = run(perm)
     assert np.array_equal(rp["x"], x[perm])
+
+
+def test_compact_layout_overflow_retry(px, oracle, monkeypatch):
+    """Compact layout (two CTAs per SM) with a deliberately small S^-1 capacity:
+    QPs whose active set outgrows it are re-solved by the generic kernel and
+    must give the same answers as the default layout."""
+    B, n, ne, ni = 32, 40, 10, 40
+    data = [px.dense.random_qp("strongly_convex", i, n, ne, ni) for i in range(B)]
+    st = {k: np.stack([d[k] for d in data]) for k in KEYS}
+
+    def run():
+        db = px.dense.DenseBatch(B, n, ne, ni)
+        db.settings.eps_abs = EPS
+        db.settings.eps_rel = 0
+        db.settings.initial_guess = px.InitialGuess.NO_INITIAL_GUESS
+        db.init(**st)
+        db.solve()
+        return db.results(), db.launch_config()
+
+    r_ref, cfg_ref = run()
+    monkeypatch.setenv("PQP_LAYOUT", "compact")
+    monkeypatch.setenv("PQP_SI_CAP", str(ne + 14))
+    r_small, cfg_small = run()
+    assert cfg_small["si_cap"] == ne + 14
+    assert cfg_small["overflow_retries"] > 0, "the test shape must overflow the forced capacity"
+    assert (r_small["info"]["status"] == 0).all() and (r_ref["info"]["status"] == 0).all()
+    assert np.abs(r_small["x"] - r_ref["x"]).max() <= 1e-7
+    for i in range(B):
+        pri, dua = kkt_residuals(data[i], r_small["x"][i], r_small["y"][i], r_small["z"][i])
+        assert pri <= EPS and dua <= EPS
