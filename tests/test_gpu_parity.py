@@ -304,7 +304,7 @@ def test_compact_layout_overflow_retry(px, oracle, monkeypatch):
     """Compact layout (two CTAs per SM) with a deliberately small S^-1 capacity:
     QPs whose active set outgrows it are re-solved by the generic kernel and
     must give the same answers as the default layout."""
-    B, n, ne, ni = 32, 40, 10, 40
+    B, n, ne, ni = 32, 20, 6, 40
     data = [px.dense.random_qp("strongly_convex", i, n, ne, ni) for i in range(B)]
     st = {k: np.stack([d[k] for d in data]) for k in KEYS}
 
@@ -319,9 +319,9 @@ def test_compact_layout_overflow_retry(px, oracle, monkeypatch):
 
     r_ref, cfg_ref = run()
     monkeypatch.setenv("PQP_LAYOUT", "compact")
-    monkeypatch.setenv("PQP_SI_CAP", str(ne + 14))
+    monkeypatch.setenv("PQP_SI_CAP", str(ne + 16))
     r_small, cfg_small = run()
-    assert cfg_small["si_cap"] == ne + 14
+    assert cfg_small["si_cap"] == ne + 16
     assert cfg_small["overflow_retries"] > 0, "the test shape must overflow the forced capacity"
     assert (r_small["info"]["status"] == 0).all() and (r_ref["info"]["status"] == 0).all()
     assert np.abs(r_small["x"] - r_ref["x"]).max() <= 1e-7
