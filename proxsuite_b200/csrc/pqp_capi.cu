@@ -159,6 +159,7 @@ fill_layout(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, bool want_m1, 
   // partial sums: NW x 32*NG for the symmetric mat-vec, NW x n for the row passes
   const int ncols = (n <= 128 && cap <= 128) ? 128 : ((n <= 160 && cap <= 160) ? 160 : 256);
   vsz[V_SCRATCH] = std::max<int>(PQP_NW * ncols, (n <= 256 && (n % 2) == 0) ? PQP_NW * n : PQP_NT);
+  vsz[V_SCRATCH] = std::max<int>(vsz[V_SCRATCH], 8 * ((std::max(n, cap) + 2) & ~1)); // 8 panel vectors of the blocked sweep
   vsz[V_RED] = PQP_NW * 16; // block_reduce: up to 10 values per warp
   int off = 0;
   for (int v = 0; v < V_COUNT; ++v) {

@@ -30,6 +30,7 @@ struct Ctx
   int vec_smem;    // 1: the vector arena is in shared memory
   int pi_smem;     // 1: P^-1 lives in shared memory (else global, read through L2)
   int si_cap;      // largest dual-block size the S^-1 storage can hold
+  int uv_ld;       // leading dimension of the 8 sweep panel vectors kept in `scratch`
   int overflow;    // set when an insertion would exceed si_cap (QP is retried by the generic kernel)
 };
 
@@ -286,7 +287,7 @@ __device__ void sym_mv_fast(const Ctx& c, const double* __restrict__ T, const do
 #pragma unroll
   for (int cc = 0; cc < NG; ++cc) scr[warp * NC + lane + 32 * cc] = acc[cc];
   __syncthreads();
-  for (int j = threadIdx.x; j < n; j += NT) {
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
     double sacc = y[j];
 #pragma unroll
     for (int w = 0; w < NW; ++w) sacc += scr[w * NC + j];
@@ -298,7 +299,7 @@ __device__ void sym_mv_fast(const Ctx& c, const double* __restrict__ T, const do
 // any n (slow, only for shapes beyond the fast paths)
 __device__ void sym_mv_generic(const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n)
 {
-  for (int j = threadIdx.x; j < n; j += NT) {
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
     double a = 0;
     const double* rj = T + (size_t)j * (size_t)(j + 1) / 2;
     for (int i = 0; i <= j; ++i) a += rj[i] * x[i];
@@ -397,33 +398,188 @@ __device__ __noinline__ void sym_rank1(double* T, const double* u, const double*
     sym_rank1_uv_generic(T, u, v, n, kfix, dfix);
 }
 
-// In-place inverse of an SPD matrix in packed storage by symmetric
-// Gauss-Jordan sweeps (Goodnight's sweep operator). Sweeping pivot k,
-//   T_ij -= T_ik T_kj / d,  T_ik = T_ik / d,  T_kk = -1/d     (d = T_kk),
-// is ONE uniform rank-one update T_ij += u_i v_j with
-//   u = col_k (u_k = d - 1),  v = -col_k / d (v_k = 1/d - 1)
-// plus the diagonal fix, so there is no dependent chain beyond the n pivots.
-// After all pivots the array holds -T^-1; the sign is folded into a last pass.
-// `u`, `v` are n-vectors of scratch. Replaces Ldlt::factorize for the blocks
-// this path inverts (linalg/dense/ldlt.hpp:718-744, factorize.hpp:91-148).
-__device__ __noinline__ void sym_sweep_invert(double* __restrict__ T, double* __restrict__ u, double* __restrict__ v, int n)
+// T[i][j] += sum_{k<4} U_k[i] * V_k[j] on the packed lower triangle (j <= i < n),
+// accumulated k = 0..3 in order (the chain four scalar sweeps would produce).
+// U_k = U + k*ldv, V_k = V + k*ldv. Rows are handled two at a time to keep the
+// register footprint below the two-CTAs-per-SM budget.
+template<int NG>
+__device__ void sym_rank4_uv(double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  PQP_SM(T);
+  PQP_SM(U);
+  PQP_SM(V);
+  double vl[4][NG];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int cc = 0; cc < NG; ++cc) {
+      const int j = lane + 32 * cc;
+      vl[k][cc] = (j < n) ? V[k * ldv + j] : 0.0;
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < NG; ++b) {
+    if (32 * b < n) {
+#pragma unroll
+      for (int rr = 0; rr < RPB; rr += 2) {
+        double a[2][NG];
+        double u[2][4];
+        double* rowp[2];
+        int ii[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          ii[r] = 32 * b + warp + NW * (rr + r);
+          if (ii[r] < n) {
+            rowp[r] = T + sym_off(ii[r]) + lane;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[r][k] = U[k * ldv + ii[r]];
+#pragma unroll
+            for (int cc = 0; cc < b; ++cc) a[r][cc] = rowp[r][32 * cc];
+            if (lane + 32 * b <= ii[r]) a[r][b] = rowp[r][32 * b];
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          if (ii[r] < n) {
+#pragma unroll
+            for (int cc = 0; cc < b; ++cc)
+              rowp[r][32 * cc] = fma(u[r][3], vl[3][cc], fma(u[r][2], vl[2][cc], fma(u[r][1], vl[1][cc], fma(u[r][0], vl[0][cc], a[r][cc]))));
+            const int j = lane + 32 * b;
+            if (j <= ii[r]) {
+              rowp[r][32 * b] = fma(u[r][3], vl[3][b], fma(u[r][2], vl[2][b], fma(u[r][1], vl[1][b], fma(u[r][0], vl[0][b], a[r][b]))));
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+__device__ void sym_rank4_uv_generic(double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < n; i += NW) {
+    double* row = T + (size_t)i * (size_t)(i + 1) / 2;
+    const double u0 = U[i], u1 = U[ldv + i], u2 = U[2 * ldv + i], u3 = U[3 * ldv + i];
+    for (int j = lane; j <= i; j += 32) {
+      row[j] = fma(u3, V[3 * ldv + j], fma(u2, V[2 * ldv + j], fma(u1, V[ldv + j], fma(u0, V[j], row[j]))));
+    }
+  }
+  __syncthreads();
+}
+__device__ __noinline__ void sym_rank4(double* T, const double* U, const double* V, int ldv, int n)
+{
+  if (n <= 128)
+    sym_rank4_uv<4>(T, U, V, ldv, n);
+  else if (n <= 160)
+    sym_rank4_uv<5>(T, U, V, ldv, n);
+  else if (n <= 256)
+    sym_rank4_uv<8>(T, U, V, ldv, n);
+  else
+    sym_rank4_uv_generic(T, U, V, ldv, n);
+}
+
+// In-place inverse of an SPD matrix in packed storage by BLOCKED symmetric
+// Gauss-Jordan sweeps (Goodnight's sweep operator, four pivots per pass over
+// the triangle). One scalar sweep on pivot k maps
+//   T_kk -> -1/d,  T_kj -> T_kj/d,  T_ij -> T_ij - T_ik T_kj / d   (d = T_kk).
+// Four consecutive sweeps touch an entry outside the pivot rows/columns K only
+// through   T_ij += sum_{k in K} U_ik V_kj,   U_ik = T^(k)_ik (column k just
+// before its own sweep), V_kj = -U_jk / d_k, and U^(k) depends only on row i of
+// the n x 4 panel T[:, K] plus the 4 x 4 pivot block. So every thread sweeps
+// its own panel row in registers (the 4 x 4 block is swept redundantly by all
+// threads), writes the finished K rows/columns straight back, stores U and V
+// (zero on K), and ONE rank-4 pass applies the rest with the same chained FMAs
+// the four scalar sweeps would have used: results match the scalar sweeps bit
+// for bit, pivot rows are scaled exactly (no cancellation for large pivots).
+// After all blocks the array holds -T^-1. `uv` is scratch for 8 vectors of
+// length ldv >= n. Replaces Ldlt::factorize for the blocks this path inverts
+// (linalg/dense/ldlt.hpp:718-744, factorize.hpp:91-148).
+__device__ __noinline__ void sym_sweep_invert(double* __restrict__ T, double* __restrict__ uv, int ldv, int n)
 {
   PQP_SM(T);
-  PQP_SM(u);
-  PQP_SM(v);
-  for (int k = 0; k < n; ++k) {
-    const double d = T[sym_off(k) + k];
-    const double dinv = 1.0 / d;
-    for (int i = threadIdx.x; i < n; i += NT) {
-      const double cv = (i >= k) ? T[sym_off(i) + k] : T[sym_off(k) + i];
-      u[i] = (i == k) ? d - 1.0 : cv;
-      v[i] = (i == k) ? dinv - 1.0 : -cv * dinv;
+  PQP_SM(uv);
+  double* const U = uv;
+  double* const V = uv + 4 * ldv;
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    const int kb = min(4, n - k0);
+    double a0[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int bq = 0; bq < 4; ++bq) {
+        const int hi = k0 + (a > bq ? a : bq), lo = k0 + (a > bq ? bq : a);
+        a0[a][bq] = (a < kb && bq < kb) ? T[sym_off(hi) + lo] : ((a == bq) ? 1.0 : 0.0);
+      }
+    }
+    __syncthreads(); // every thread holds the pivot block before anyone overwrites it
+    _Pragma("unroll 1") for (int i = threadIdx.x; i < n; i += NT) {
+      double a[4][4], p[4], ui[4], vi[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[q][r] = a0[q][r];
+      }
+      const int ai = i - k0; // position of this row inside the pivot block when 0 <= ai < kb
+      const bool inK = (ai >= 0) && (ai < kb);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int col = k0 + l;
+        p[l] = (l < kb) ? ((i >= col) ? T[sym_off(i) + col] : T[sym_off(col) + i]) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < kb) {
+          const double inv = 1.0 / a[k][k];
+          double vK[4];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) vK[l] = -a[k][l] * inv;
+          const double pk = p[k];
+          if (ai == k) {
+            ui[k] = 0.0;
+            vi[k] = 0.0;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? -inv : p[l] * inv;
+          } else {
+            ui[k] = inK ? 0.0 : pk;
+            vi[k] = inK ? 0.0 : -pk * inv;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? pk * inv : fma(pk, vK[l], p[l]);
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (m != k) {
+              const double amk = a[m][k];
+#pragma unroll
+              for (int l = 0; l < 4; ++l) a[m][l] = (l == k) ? amk * inv : fma(amk, vK[l], a[m][l]);
+            }
+          }
+#pragma unroll
+          for (int l = 0; l < 4; ++l) a[k][l] = (l == k) ? -inv : a[k][l] * inv;
+        } else {
+          ui[k] = 0.0;
+          vi[k] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int col = k0 + l;
+        if (l < kb) {
+          if (i >= col)
+            T[sym_off(i) + col] = p[l];
+          else if (!inK)
+            T[sym_off(col) + i] = p[l];
+        }
+        U[l * ldv + i] = ui[l];
+        V[l * ldv + i] = vi[l];
+      }
     }
     __syncthreads();
-    sym_rank1(T, u, v, n, k, -dinv);
+    sym_rank4(T, U, V, ldv, n);
   }
   const int tot = sym_off(n);
-  for (int e = threadIdx.x; e < tot; e += NT) T[e] = -T[e];
+  _Pragma("unroll 1") for (int e = threadIdx.x; e < tot; e += NT) T[e] = -T[e];
   __syncthreads();
 }
 
@@ -554,7 +710,7 @@ __device__ void mat_pass_fast(const Ctx& c, RowSrc rs, int r0, int r1, const dou
     if (lane < n2) reinterpret_cast<double2*>(scr)[warp * n2 + lane] = acc0;
     if (l1) reinterpret_cast<double2*>(scr)[warp * n2 + lane + 32] = acc1;
     __syncthreads();
-    for (int j = threadIdx.x; j < n; j += NT) {
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
       double sacc = 0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) sacc += scr[w * n + j];
@@ -589,7 +745,7 @@ __device__ void rows_axpy_t(const Ctx& c, RowSrc rs, int r0, int r1, const doubl
 {
   PQP_VECS(c);
   const int n = c.n;
-  for (int j = threadIdx.x; j < n; j += NT) {
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
     double acc = 0;
     for (int r = r0; r < r1; ++r) {
       int bk, idx;
@@ -625,7 +781,7 @@ __device__ void apply_Pinv(const Ctx& c, const double* v, double* y)
 {
   PQP_VECS(c);
   if (c.hess != PQP_HESSIAN_DENSE) {
-    for (int j = threadIdx.x; j < c.n; j += NT) y[j] = v[j] * v_d1inv[j];
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) y[j] = v[j] * v_d1inv[j];
     __syncthreads();
     return;
   }
@@ -647,14 +803,14 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
   const int ns = c.ns;
   if (ns == 0) {
     apply_Pinv(c, b1, v_t1);
-    for (int j = threadIdx.x; j < c.n; j += NT) ox[j] = v_t1[j];
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) ox[j] = v_t1[j];
     __syncthreads();
     return;
   }
   apply_Pinv(c, b1, v_t1);
   RowSrc slots{ nullptr, nullptr, 1 };
   mat_pass(c, slots, 0, ns, v_t1, v_s1, nullptr, nullptr, nullptr, 1.0);
-  for (int s = threadIdx.x; s < ns; s += NT) v_s1[s] -= b2[s];
+  _Pragma("unroll 1") for (int s = threadIdx.x; s < ns; s += NT) v_s1[s] -= b2[s];
   __syncthreads();
   sym_mv(c, c.Si, v_s1, os, ns, true);
   mat_pass(c, slots, 0, ns, nullptr, nullptr, os, v_t2, b1, -1.0);
@@ -670,13 +826,13 @@ __device__ void gram_row(Ctx& c, int s)
   int bk, idx;
   const double* row = get_row(c, slots, s, bk, idx);
   // stage the row in shared memory (rows of C_s live in global memory)
-  for (int j = threadIdx.x; j < c.n; j += NT) v_t2[j] = row ? row[j] : ((j == bk) ? v_is[bk] : 0.0);
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) v_t2[j] = row ? row[j] : ((j == bk) ? v_is[bk] : 0.0);
   __syncthreads();
   row = v_t2;
   apply_Pinv(c, row, v_t1);
   mat_pass(c, slots, 0, s + 1, v_t1, v_s3, nullptr, nullptr, nullptr, 1.0);
   const int ids = row_id(c, s);
-  for (int j = threadIdx.x; j <= s; j += NT) c.G[gidx(ids, row_id(c, j))] = v_s3[j];
+  _Pragma("unroll 1") for (int j = threadIdx.x; j <= s; j += NT) c.G[gidx(ids, row_id(c, j))] = v_s3[j];
 }
 
 // Append dual slot s == c.ns (already registered in slot_cons) with proximal
@@ -699,11 +855,11 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu)
   if (s > 0) {
     sym_mv(c, c.Si, v_s3, v_s1, s, true);
     double part = 0;
-    for (int j = threadIdx.x; j < s; j += NT) part += v_s3[j] * v_s1[j];
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) part += v_s3[j] * v_s1[j];
     delta -= block_sum1(c, part);
     const double dinv = 1.0 / delta;
     double* row = c.Si + sym_off(s);
-    for (int j = threadIdx.x; j < s; j += NT) {
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) {
       const double wj = v_s1[j] * dinv;
       v_s2[j] = wj;
       row[j] = -wj;
@@ -726,11 +882,11 @@ __device__ __noinline__ void delete_slot(Ctx& c, int k)
   PQP_VECS(c);
   const int ns = c.ns;
   double* T = c.Si;
-  for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = (i >= k) ? T[sym_off(i) + k] : T[sym_off(k) + i];
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = (i >= k) ? T[sym_off(i) + k] : T[sym_off(k) + i];
   __syncthreads();
   const double sinv = -1.0 / v_s1[k];
   __syncthreads();
-  for (int i = threadIdx.x; i < ns; i += NT) {
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
     const double q = (i == k) ? 0.0 : v_s1[i]; // row / column k are dropped below
     v_s2[i] = q;
     v_s3[i] = q * sinv;
@@ -792,7 +948,7 @@ __device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_i
     for (int j = lane; j <= s; j += 32) row[j] = c.G[gidx(ids, row_id(c, j))] + ((j == s) ? (s < c.ne ? mu_eq : mu_in) : 0.0);
   }
   __syncthreads();
-  sym_sweep_invert(c.Si, v_s1, v_s2, ns);
+  sym_sweep_invert(c.Si, v_scratch, c.uv_ld, ns);
 }
 
 // P^-1 = (Hs + rho I)^-1, explicit. Replaces the x-block part of
@@ -802,7 +958,7 @@ __device__ __noinline__ void build_Pi(Ctx& c, double rho)
   PQP_VECS(c);
   const int n = c.n;
   if (c.hess != PQP_HESSIAN_DENSE) {
-    for (int j = threadIdx.x; j < n; j += NT) {
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
       double h = (c.hess == PQP_HESSIAN_DIAGONAL) ? c.Hs[(size_t)j * n + j] : 0.0;
       v_d1inv[j] = 1.0 / (h + rho);
     }
@@ -820,10 +976,10 @@ __device__ __noinline__ void build_Pi(Ctx& c, double rho)
     for (int j = lane; j <= i; j += 32) row[j] = h[j] + ((j == i) ? rho : 0.0);
   }
   __syncthreads();
-  sym_sweep_invert(work, v_t1, v_t2, n);
+  sym_sweep_invert(work, v_scratch, c.uv_ld, n);
   if (!c.pi_smem) {
     const int tot = sym_off(n);
-    for (int e = threadIdx.x; e < tot; e += NT) c.Pi[e] = work[e];
+    _Pragma("unroll 1") for (int e = threadIdx.x; e < tot; e += NT) c.Pi[e] = work[e];
     __syncthreads();
   }
 }
@@ -866,12 +1022,12 @@ __device__ __noinline__ double kkt_residual(const Ctx& c, const Scal& sc)
   PQP_VECS(c);
   const int n = c.n, ne = c.ne, ns = c.ns;
   // per-constraint coefficient of the transposed product: dz of active rows, 0 otherwise
-  for (int i = threadIdx.x; i < c.nc; i += NT) {
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < c.nc; i += NT) {
     const int s = c.cons_slot[i];
     v_dz[i] = (s >= 0) ? v_ds[s] : 0.0;
   }
   if (c.hess != PQP_HESSIAN_DENSE) {
-    for (int j = threadIdx.x; j < n; j += NT) v_hdx[j] = (c.hess == PQP_HESSIAN_DIAGONAL) ? c.Hs[(size_t)j * n + j] * v_dx[j] : 0.0;
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) v_hdx[j] = (c.hess == PQP_HESSIAN_DIAGONAL) ? c.Hs[(size_t)j * n + j] * v_dx[j] : 0.0;
   }
   __syncthreads();
   if (c.hess == PQP_HESSIAN_DENSE) mat_pass(c, RowSrc{ c.Hs, nullptr, 0 }, 0, n, v_dx, v_hdx, nullptr, nullptr, nullptr, 1.0);
@@ -879,12 +1035,12 @@ __device__ __noinline__ double kkt_residual(const Ctx& c, const Scal& sc)
   mat_pass(c, RowSrc{ c.As, nullptr, 0 }, 0, ne, v_dx, v_adx, v_ds, v_atdy, nullptr, 1.0);
   mat_pass(c, RowSrc{ nullptr, nullptr, 3 }, 0, c.nc, v_dx, v_cdx, v_dz, v_ctdz, nullptr, 1.0);
   double m = 0;
-  for (int j = threadIdx.x; j < n; j += NT) {
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
     double e = v_rx[j] - (v_hdx[j] + sc.rho * v_dx[j] + v_atdy[j] + v_ctdz[j]);
     v_ex[j] = e;
     m = nanmax(m, fabs(e));
   }
-  for (int s = threadIdx.x; s < ns; s += NT) {
+  _Pragma("unroll 1") for (int s = threadIdx.x; s < ns; s += NT) {
     double e;
     if (s < ne)
       e = v_rs[s] - (v_adx[s] - sc.mu_eq * v_ds[s]);
@@ -926,8 +1082,8 @@ __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_setting
       ++it;
       tp = PROF_T0();
       solve_kkt(c, v_ex, v_es, v_ex, v_es);
-      for (int j = threadIdx.x; j < c.n; j += NT) v_dx[j] += v_ex[j];
-      for (int s = threadIdx.x; s < c.ns; s += NT) v_ds[s] += v_es[s];
+      _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) v_dx[j] += v_ex[j];
+      _Pragma("unroll 1") for (int s = threadIdx.x; s < c.ns; s += NT) v_ds[s] += v_es[s];
       __syncthreads();
       PROF_ADD(PH_SOLVE, tp);
       tp = PROF_T0();
@@ -947,8 +1103,8 @@ __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_setting
     }
     break;
   }
-  for (int j = threadIdx.x; j < c.n; j += NT) v_rx[j] = 0;
-  for (int s = threadIdx.x; s < c.cap; s += NT) v_rs[s] = 0;
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) v_rx[j] = 0;
+  _Pragma("unroll 1") for (int s = threadIdx.x; s < c.cap; s += NT) v_rs[s] = 0;
   __syncthreads();
 }
 
@@ -996,7 +1152,7 @@ __device__ __noinline__ void global_passes(Ctx& c, bool primal, bool dual)
     if (c.hess == PQP_HESSIAN_DENSE) {
       mat_pass(c, RowSrc{ c.Hs, nullptr, 0 }, 0, n, v_x, v_t1, nullptr, nullptr, nullptr, 1.0);
     } else {
-      for (int j = threadIdx.x; j < n; j += NT) v_t1[j] = (c.hess == PQP_HESSIAN_DIAGONAL) ? c.Hs[(size_t)j * n + j] * v_x[j] : 0.0;
+      _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) v_t1[j] = (c.hess == PQP_HESSIAN_DIAGONAL) ? c.Hs[(size_t)j * n + j] * v_x[j] : 0.0;
       __syncthreads();
     }
   }
@@ -1013,14 +1169,14 @@ __device__ __noinline__ void global_primal_residual(Ctx& c, const Scal& sc, cons
   const double* de = v_delta + n;
   const double* di = v_delta + n + ne;
   const double* db = v_delta + n + ne + ni;
-  for (int i = threadIdx.x; i < ne; i += NT) {
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ne; i += NT) {
     double v = v_se[i] / de[i];
     mx[0] = nanmax(mx[0], fabs(v));
     v -= v_b[i];
     mx[2] = nanmax(mx[2], fabs(v));
     v_se[i] = v; // unscaled Ax - b, rescaled below
   }
-  for (int i = threadIdx.x; i < nc; i += NT) {
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < nc; i += NT) {
     double v;
     if (i < ni) {
       v = v_rup[i] / di[i];
@@ -1050,10 +1206,10 @@ __device__ __noinline__ void global_primal_residual(Ctx& c, const Scal& sc, cons
     mat_pass(c, RowSrc{ c.Am, nullptr, 0 }, 0, ne, nullptr, nullptr, v_se, v_ex, nullptr, 1.0);
     mat_pass(c, RowSrc{ c.Cm, nullptr, 0 }, 0, ni, nullptr, nullptr, v_si, v_ex, v_ex, 1.0);
     double m = 0;
-    for (int j = threadIdx.x; j < n; j += NT) m = nanmax(m, fabs(v_ex[j]));
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) m = nanmax(m, fabs(v_ex[j]));
     g.pri_lhs = block_max1(c, m);
   }
-  for (int i = threadIdx.x; i < ne; i += NT) v_se[i] *= de[i];
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ne; i += NT) v_se[i] *= de[i];
   __syncthreads();
 }
 
@@ -1067,7 +1223,7 @@ __device__ __noinline__ void global_dual_residual(Ctx& c, const Scal& sc, Glob& 
   double sm[6] = { 0, 0, 0, 0, 0, 0 }; // g.x, xHx, b.y, zu, zl, (unused)
   double mx[4] = { 0, 0, 0, 0 };       // rhs0, rhs1, rhs3, lhs
   const double inf_b = 1.3407807929942596e+154; // sqrt(DBL_MAX), helpers/common.hpp:20-24
-  for (int j = threadIdx.x; j < n; j += NT) {
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
     const double dxc = v_delta[j] * cs;
     double hx = v_t1[j], aty = v_t2[j], ctz = v_t3[j];
     double zb = c.box ? v_z[ni + j] * v_is[j] : 0.0;
@@ -1085,8 +1241,8 @@ __device__ __noinline__ void global_dual_residual(Ctx& c, const Scal& sc, Glob& 
   }
   const double* de = v_delta + n;
   const double* di = v_delta + n + ne;
-  for (int i = threadIdx.x; i < ne; i += NT) sm[2] += v_b[i] * (v_y[i] * de[i] / cs);
-  for (int i = threadIdx.x; i < nc; i += NT) {
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ne; i += NT) sm[2] += v_b[i] * (v_y[i] * de[i] / cs);
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < nc; i += NT) {
     double zu_ = v_z[i] * di[i] / cs; // delta laid out [x | eq | in | box]: di[i] covers box too
     if (c.act_up[i]) sm[3] += zu_ * fmin(v_u[i], inf_b);
     if (c.act_low[i]) sm[4] += zu_ * fmax(v_l[i], -inf_b);
@@ -1127,14 +1283,14 @@ __device__ __noinline__ LsBase ls_base(const Ctx& c, const Scal& sc, const pqp_s
   const bool gpdal = S.merit_function_type == PQP_MERIT_GPDAL;
   double sm[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
   double dummy[1] = { 0 };
-  for (int j = threadIdx.x; j < n; j += NT) {
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
     double dxj = v_dx[j];
     sm[0] += dxj * v_hdx[j];
     sm[1] += dxj * dxj;
     sm[2] += v_x[j] * v_hdx[j];
     sm[3] += (sc.rho * (v_x[j] - v_xp[j]) + v_gs[j]) * dxj;
   }
-  for (int i = threadIdx.x; i < ne; i += NT) {
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ne; i += NT) {
     double ad = v_adx[i];
     double e = ad - v_ds[i] * sc.mu_eq;
     sm[4] += ad * ad;
@@ -1143,7 +1299,7 @@ __device__ __noinline__ LsBase ls_base(const Ctx& c, const Scal& sc, const pqp_s
     sm[7] += e * v_se[i];
   }
   if (gpdal) {
-    for (int i = threadIdx.x; i < nc; i += NT) {
+    _Pragma("unroll 1") for (int i = threadIdx.x; i < nc; i += NT) {
       sm[8] += v_dz[i] * v_dz[i];
       sm[9] += v_dz[i] * v_z[i];
     }
@@ -1203,7 +1359,7 @@ __device__ __noinline__ double primal_dual_ls(Ctx& c, const Scal& sc, const pqp_
   LsBase base = ls_base(c, sc, S);
   if (threadIdx.x == 0) c.iscratch[2 * NW] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < nc; i += NT) {
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < nc; i += NT) {
     const double cd = v_cdx[i];
     if (cd != 0.0) {
       double a1 = -v_rup[i] / (cd + eps);
@@ -1216,7 +1372,7 @@ __device__ __noinline__ double primal_dual_ls(Ctx& c, const Scal& sc, const pqp_
   const int n_alpha = c.iscratch[2 * NW];
   // thread 0 of the last warp additionally evaluates alpha = 0
   double best_pos_alpha = INFINITY, best_pos_grad = 0, best_neg_alpha = 0, best_neg_grad = 0;
-  for (int k = threadIdx.x; k < n_alpha + 1; k += NT) {
+  _Pragma("unroll 1") for (int k = threadIdx.x; k < n_alpha + 1; k += NT) {
     const double al = (k < n_alpha) ? v_alphas[k] : 0.0;
     double a, b;
     ls_eval(c, sc, S, base, al, a, b);
@@ -1333,14 +1489,14 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
     }
     __syncthreads();
     if (A.lay.in_smem[PA_AS]) {
-      for (int i = tid; i < ne * n; i += NT) c.As[i] = Asg[i];
+      _Pragma("unroll 1") for (int i = tid; i < ne * n; i += NT) c.As[i] = Asg[i];
     }
-    for (int j = tid; j < n; j += NT) v_gs[j] = P.gs[(size_t)q * n + j];
-    for (int j = tid; j < ne; j += NT) {
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_gs[j] = P.gs[(size_t)q * n + j];
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) {
       v_bs[j] = P.bs[(size_t)q * ne + j];
       v_b[j] = P.b[(size_t)q * ne + j];
     }
-    for (int j = tid; j < nc; j += NT) {
+    _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) {
       v_us[j] = P.us[(size_t)q * nc + j];
       v_ls[j] = P.ls[(size_t)q * nc + j];
       if (j < ni) {
@@ -1355,9 +1511,9 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
       c.act_low[j] = 0;
     }
     if (c.box) {
-      for (int j = tid; j < n; j += NT) v_is[j] = P.is[(size_t)q * n + j];
+      _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_is[j] = P.is[(size_t)q * n + j];
     }
-    for (int j = tid; j < n + ne + nc; j += NT) v_delta[j] = P.delta[(size_t)q * (n + ne + nc) + j];
+    _Pragma("unroll 1") for (int j = tid; j < n + ne + nc; j += NT) v_delta[j] = P.delta[(size_t)q * (n + ne + nc) + j];
     if (tid == 0) {
       c.c_scale = P.c[q];
       c.ns = 0;
@@ -1386,24 +1542,24 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
 
   // ---- initial iterate (solver.hpp:1125-1377) --------------------------------
   if (prm.start_mode == PQP_START_WARM || prm.start_mode == PQP_START_WARM_KEEP) {
-    for (int j = tid; j < n; j += NT) v_x[j] = A.p.x[(size_t)q * n + j] / dlx[j];
-    for (int j = tid; j < ne; j += NT) v_y[j] = A.p.y[(size_t)q * ne + j] / dle[j] * cs;
-    for (int j = tid; j < nc; j += NT) v_z[j] = A.p.z[(size_t)q * nc + j] / dli[j] * cs;
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_x[j] = A.p.x[(size_t)q * n + j] / dlx[j];
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_y[j] = A.p.y[(size_t)q * ne + j] / dle[j] * cs;
+    _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) v_z[j] = A.p.z[(size_t)q * nc + j] / dli[j] * cs;
   } else {
-    for (int j = tid; j < n; j += NT) v_x[j] = 0;
-    for (int j = tid; j < ne; j += NT) v_y[j] = 0;
-    for (int j = tid; j < nc; j += NT) v_z[j] = 0;
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_x[j] = 0;
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_y[j] = 0;
+    _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) v_z[j] = 0;
   }
-  for (int j = tid; j < n; j += NT) {
+  _Pragma("unroll 1") for (int j = tid; j < n; j += NT) {
     v_rx[j] = 0;
     v_dx[j] = 0;
   }
-  for (int j = tid; j < c.cap; j += NT) {
+  _Pragma("unroll 1") for (int j = tid; j < c.cap; j += NT) {
     v_rs[j] = 0;
     v_ds[j] = 0;
   }
-  for (int j = tid; j < ne; j += NT) v_se[j] = 0;
-  for (int j = tid; j < nc; j += NT) {
+  _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_se[j] = 0;
+  _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) {
     v_si[j] = 0;
     v_dz[j] = 0;
   }
@@ -1420,28 +1576,28 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
 
   if (prm.start_mode == PQP_START_EQ_GUESS) {
     // helpers.hpp:201-228
-    for (int j = tid; j < n; j += NT) v_rx[j] = -v_gs[j];
-    for (int j = tid; j < ne; j += NT) v_rs[j] = v_bs[j];
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_rx[j] = -v_gs[j];
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_rs[j] = v_bs[j];
     __syncthreads();
     iterative_solve(c, sc, S, 1.0);
-    for (int j = tid; j < n; j += NT) {
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) {
       v_x[j] = v_dx[j];
       v_dx[j] = 0;
     }
-    for (int j = tid; j < ne; j += NT) {
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) {
       v_y[j] = v_ds[j];
       v_ds[j] = 0;
     }
     __syncthreads();
   } else if (prm.start_mode == PQP_START_WARM || prm.start_mode == PQP_START_WARM_KEEP) {
     // active set := { i : z_i != 0 } (solver.hpp:1300-1309)
-    for (int i = tid; i < nc; i += NT) {
+    _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
       c.act_up[i] = (v_z[i] != 0.0);
       c.act_low[i] = 0;
     }
     __syncthreads();
     active_set_change(c, sc);
-    for (int i = tid; i < nc; i += NT) c.act_up[i] = 0;
+    _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) c.act_up[i] = 0;
     __syncthreads();
   }
   const bool overflow_at_start = c.overflow != 0;
@@ -1456,7 +1612,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
   g.dua_lhs = g.dua_rhs0 = g.dua_rhs1 = g.dua_rhs3 = g.gap = g.rhs_gap = 0;
   const double dual_rhs2 = [&]() {
     double m = 0;
-    for (int j = tid; j < n; j += NT) m = nanmax(m, fabs(v_gs[j] / (dlx[j] * cs)));
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) m = nanmax(m, fabs(v_gs[j] / (dlx[j] * cs)));
     return block_max1(c, m);
   }(); // |model.g|_inf (helpers.hpp:651)
   double info_pri = 0, info_dua = 0, info_gap = 0;
@@ -1504,10 +1660,10 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
     }
     sc.iter_ext += 1;
     // x_prev..; shifted residuals (solver.hpp:1517-1559)
-    for (int j = tid; j < n; j += NT) v_xp[j] = v_x[j];
-    for (int j = tid; j < ne; j += NT) v_yp[j] = v_y[j];
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_xp[j] = v_x[j];
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_yp[j] = v_y[j];
     const double ag = (S.merit_function_type == PQP_MERIT_GPDAL) ? S.alpha_gpdal : 1.0;
-    for (int i = tid; i < nc; i += NT) {
+    _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
       const double zi = v_z[i];
       v_zp[i] = zi;
       double v = v_rup[i] * dli[i]; // scaled C x (box: scaled x-bound residual)
@@ -1534,7 +1690,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
           if (expired) break;
         }
         // -- Newton step (solver.hpp:756-869)
-        for (int i = tid; i < nc; i += NT) {
+        _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
           c.act_up[i] = v_rup[i] >= 0.0;
           c.act_low[i] = v_si[i] <= 0.0;
         }
@@ -1549,10 +1705,10 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
         if (nq > 0) {
           mat_pass(c, RowSrc{ nullptr, c.list2, 2 }, 0, nq, nullptr, nullptr, v_z, v_q, nullptr, 1.0);
         } else {
-          for (int j = tid; j < n; j += NT) v_q[j] = 0;
+          _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_q[j] = 0;
         }
-        for (int j = tid; j < n; j += NT) v_rx[j] = -v_dual[j] + v_q[j];
-        for (int s = tid; s < c.ns; s += NT) {
+        _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_rx[j] = -v_dual[j] + v_q[j];
+        _Pragma("unroll 1") for (int s = tid; s < c.ns; s += NT) {
           if (s < ne) {
             v_rs[s] = -v_se[s];
           } else {
@@ -1566,13 +1722,13 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
         __syncthreads();
         iterative_solve(c, sc, S, eps_int);
         // un-permute dz; Cdx, CTdz (solver.hpp:860-967)
-        for (int i = tid; i < nc; i += NT) {
+        _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
           const int s = c.cons_slot[i];
           const double dzi = (s >= 0) ? v_ds[s] : -v_z[i];
           v_dz[i] = dzi;
           if (S.merit_function_type == PQP_MERIT_GPDAL) v_cdx[i] += (S.alpha_gpdal - 1.0) * sc.mu_in * dzi;
         }
-        for (int j = tid; j < n; j += NT) v_ctdz[j] -= v_q[j];
+        _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_ctdz[j] -= v_q[j];
         __syncthreads();
         double alpha = 1.0;
         tph = PROF_T0();
@@ -1581,9 +1737,9 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
         // |alpha dw|_inf
         {
           double m = 0;
-          for (int j = tid; j < n; j += NT) m = nanmax(m, fabs(v_dx[j]));
-          for (int j = tid; j < ne; j += NT) m = nanmax(m, fabs(v_ds[j]));
-          for (int i = tid; i < nc; i += NT) m = nanmax(m, fabs(v_dz[i]));
+          _Pragma("unroll 1") for (int j = tid; j < n; j += NT) m = nanmax(m, fabs(v_dx[j]));
+          _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) m = nanmax(m, fabs(v_ds[j]));
+          _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) m = nanmax(m, fabs(v_dz[i]));
           m = block_max1(c, m);
           if (m * fabs(alpha) < 1e-11 && it_in > 0) {
             sc.iter += it_in + 1;
@@ -1594,7 +1750,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
         double sm[6] = { 0, 0, 0, 0, 0, 0 }; // lb1 (primal inf), gdx
         double mx[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
         // mx: 0 err_in | 1 |dy|u 2 |dz|u 3 |ATdy+CTdz|u 4 |dy|s,|dz|s any nonzero | 5 |dx|u 6 |Adx|u 7 |Hdx|u 8 first_cond violation 9 spare
-        for (int j = tid; j < n; j += NT) {
+        _Pragma("unroll 1") for (int j = tid; j < n; j += NT) {
           const double dxj = v_dx[j];
           v_x[j] += alpha * dxj;
           double dr = v_dual[j] + alpha * (sc.rho * dxj + ((c.hess == PQP_HESSIAN_ZERO) ? 0.0 : v_hdx[j]) + v_atdy[j] + v_ctdz[j]);
@@ -1607,7 +1763,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
           mx[7] = nanmax(mx[7], fabs(v_hdx[j] / dxc));
           sm[1] += dxj * v_gs[j];
         }
-        for (int i = tid; i < ne; i += NT) {
+        _Pragma("unroll 1") for (int i = tid; i < ne; i += NT) {
           const double dyi = v_ds[i];
           double sev = v_se[i] + alpha * (v_adx[i] - sc.mu_eq * dyi);
           v_se[i] = sev;
@@ -1618,7 +1774,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
           mx[1] = nanmax(mx[1], fabs(dyi * dle[i] / cs));
           mx[6] = nanmax(mx[6], fabs(v_adx[i] / dle[i]));
         }
-        for (int i = tid; i < nc; i += NT) {
+        _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
           const double dzi = v_dz[i], cd = v_cdx[i];
           const double ru = v_rup[i] + alpha * cd;
           const double sl = v_si[i] + alpha * cd;
@@ -1646,7 +1802,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
           {
             double bound = mx[5] * S.eps_dual_inf;
             double viol = 0;
-            for (int i = tid; i < nc; i += NT) {
+            _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
               const double v = v_cdx[i] / dli[i]; // unscaled (box entries use delta_box)
               bool ok = true;
               if (v_us[i] <= 1e20 && v_ls[i] >= -1e20)
@@ -1684,21 +1840,21 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
     if (expired) break;
     if ((sc.status == PQP_PRIMAL_INFEASIBLE && !S.primal_infeasibility_solving) || sc.status == PQP_DUAL_INFEASIBLE) {
       // certificate of infeasibility: the (already unscaled, quirk 4) step
-      for (int j = tid; j < n; j += NT) v_x[j] = v_dx[j] * dlx[j];
-      for (int j = tid; j < ne; j += NT) v_y[j] = v_ds[j] * dle[j] / cs;
-      for (int i = tid; i < nc; i += NT) v_z[i] = v_dz[i] * dli[i] / cs;
+      _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_x[j] = v_dx[j] * dlx[j];
+      _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_y[j] = v_ds[j] * dle[j] / cs;
+      _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) v_z[i] = v_dz[i] * dli[i] / cs;
       __syncthreads();
       infeasible_exit = true;
       break;
     }
     if (scaled_eps == S.eps_abs && S.primal_infeasibility_solving && sc.status == PQP_PRIMAL_INFEASIBLE) {
       // solver.hpp:1581-1595
-      for (int j = tid; j < c.cap; j += NT) v_s1[j] = 1.0;
+      _Pragma("unroll 1") for (int j = tid; j < c.cap; j += NT) v_s1[j] = 1.0;
       __syncthreads();
       mat_pass(c, RowSrc{ c.Am, nullptr, 0 }, 0, ne, nullptr, nullptr, v_s1, v_t1, nullptr, 1.0);
       mat_pass(c, RowSrc{ c.Cm, nullptr, 0 }, 0, ni, nullptr, nullptr, v_s1, v_t1, v_t1, 1.0);
       double m = 0;
-      for (int j = tid; j < n; j += NT) m = nanmax(m, fabs(v_t1[j] + (c.box ? v_is[j] : 0.0)));
+      _Pragma("unroll 1") for (int j = tid; j < n; j += NT) m = nanmax(m, fabs(v_t1[j] + (c.box ? v_is[j] : 0.0)));
       scaled_eps = block_max1(c, m) * S.eps_abs;
     }
     tph = PROF_T0();
@@ -1729,8 +1885,8 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
         bcl_eta_ext *= pow(sc.mu_in, S.beta_bcl);
         bcl_eta_in = fmax(bcl_eta_in * sc.mu_in, eps_in_min);
       } else {
-        for (int j = tid; j < ne; j += NT) v_y[j] = v_yp[j];
-        for (int i = tid; i < nc; i += NT) v_z[i] = v_zp[i];
+        _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_y[j] = v_yp[j];
+        _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) v_z[i] = v_zp[i];
         __syncthreads();
         dual_done = false;
         new_mu_in = fmax(sc.mu_in * S.mu_update_factor, S.mu_min_in);
@@ -1794,16 +1950,16 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
   double* seo = A.p.se + (size_t)q * ne;
   double* sio = A.p.si + (size_t)q * nc;
   const bool unscale_s = S.primal_infeasibility_solving && sc.status == PQP_PRIMAL_INFEASIBLE;
-  for (int j = tid; j < n; j += NT) {
+  _Pragma("unroll 1") for (int j = tid; j < n; j += NT) {
     const double xu = v_x[j] * dlx[j];
     v_t1[j] = xu;
     xo[j] = xu;
   }
-  for (int j = tid; j < ne; j += NT) {
+  _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) {
     yo[j] = v_y[j] * dle[j] / cs;
     seo[j] = unscale_s ? v_se[j] / dle[j] : v_se[j];
   }
-  for (int i = tid; i < nc; i += NT) {
+  _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
     zo[i] = v_z[i] * dli[i] / cs;
     sio[i] = unscale_s ? v_si[i] / dli[i] : v_si[i];
   }
@@ -1815,12 +1971,12 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
     if (c.hess == PQP_HESSIAN_DENSE) {
       mat_pass(c, RowSrc{ c.Hm, nullptr, 0 }, 0, n, v_t1, v_t2, nullptr, nullptr, nullptr, 1.0);
     } else {
-      for (int j = tid; j < n; j += NT) v_t2[j] = c.Hm[(size_t)j * n + j] * v_t1[j];
+      _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_t2[j] = c.Hm[(size_t)j * n + j] * v_t1[j];
       __syncthreads();
     }
     double part = 0;
     const double* gm = A.p.g + (size_t)q * n;
-    for (int j = tid; j < n; j += NT) part += v_t1[j] * (0.5 * v_t2[j] + gm[j]);
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) part += v_t1[j] * (0.5 * v_t2[j] + gm[j]);
     obj = block_sum1(c, part);
   }
   if (tid == 0) {
@@ -1864,6 +2020,7 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArg
     c.vec_smem = L.in_smem[PA_VEC];
     c.pi_smem = L.in_smem[PA_M1];
     c.si_cap = L.si_cap;
+    c.uv_ld = ((A.d.n > A.d.cap ? A.d.n : A.d.cap) + 2) & ~1;
     c.overflow = 0;
     double* ws = A.ws + (size_t)blockIdx.x * (size_t)L.ws_doubles;
     auto place = [&](int id) -> double* { return (L.in_smem[id] ? smem_dyn : ws) + L.off[id]; };
