@@ -161,6 +161,7 @@ fill_layout(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, bool want_m1, 
   vsz[V_SCRATCH] = std::max<int>(PQP_NW * ncols, (n <= 256 && (n % 2) == 0) ? PQP_NW * n : PQP_NT);
   vsz[V_SCRATCH] = std::max<int>(vsz[V_SCRATCH], 8 * ((std::max(n, cap) + 2) & ~1)); // 8 panel vectors of the blocked sweep
   vsz[V_RED] = PQP_NW * 16; // block_reduce: up to 10 values per warp
+  vsz[V_KT] = 2;
   int off = 0;
   for (int v = 0; v < V_COUNT; ++v) {
     L.voff[v] = off;
@@ -203,6 +204,89 @@ fill_layout(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, bool want_m1, 
   return 0;
 }
 
+// Doubles of the 32 x 32 tile storage (row stride 33) of a symmetric matrix of capacity cap
+// (pqp_fast_body.inl: ts_extent(cap, cap)).
+int64_t
+tile_doubles(int64_t cap)
+{
+  const int64_t nb = (cap + 31) / 32;
+  if (nb == 0) return 2;
+  const int64_t rows_last = cap - 32 * (nb - 1);
+  return ((nb - 1) * nb / 2) * (32 * 33) + nb * rows_last * 33 + 2;
+}
+
+// Tile layout (kind 1) of the specialised kernel: vectors + S^-1 (tile storage, capacity
+// si_cap <= 128) in shared memory; P^-1 (n x ldn), Bt (n x ldb) and G in the per-CTA workspace.
+int
+fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_cap, int ctas)
+{
+  std::memset(&L, 0, sizeof(L));
+  const int n = d.n, ne = d.ne, nc = d.nc, cap = d.cap;
+  auto rnd = [](int64_t v) { return (v + 1) & ~int64_t(1); };
+  const int sc = si_cap + 2; // slot-indexed vectors
+  int vsz[V_COUNT];
+  for (int& v : vsz) v = 0;
+  vsz[V_X] = n; vsz[V_Y] = ne; vsz[V_Z] = nc; vsz[V_XP] = n; vsz[V_YP] = ne; vsz[V_ZP] = nc;
+  vsz[V_DX] = n; vsz[V_DS] = sc; vsz[V_DZ] = nc;
+  vsz[V_RX] = n; vsz[V_RS] = sc; vsz[V_EX] = n; vsz[V_ES] = sc;
+  vsz[V_DUAL] = n; vsz[V_SE] = ne + nc + 2; vsz[V_RUP] = 0; vsz[V_SI] = nc; // [A x; C x] contiguous
+  vsz[V_HDX] = n; vsz[V_ADX] = ne + nc + 2; vsz[V_ATDY] = n; vsz[V_CDX] = 0; vsz[V_CTDZ] = 2; vsz[V_Q] = n; // [A dx; C dx] contiguous
+  vsz[V_GS] = n; vsz[V_BS] = ne; vsz[V_US] = nc; vsz[V_LS] = nc; vsz[V_IS] = 2; vsz[V_DELTA] = n + ne + nc;
+  vsz[V_B] = ne; vsz[V_U] = nc; vsz[V_L] = nc;
+  vsz[V_D1INV] = 2; vsz[V_DSV] = 2; vsz[V_DSINV] = 2;
+  vsz[V_T1] = n; vsz[V_T2] = n; vsz[V_T3] = n;
+  vsz[V_S1] = sc; vsz[V_S2] = sc; vsz[V_S3] = sc; vsz[V_S4] = sc;
+  vsz[V_ALPHAS] = 2 * nc + 2; vsz[V_GRADS] = 4;
+  const int uv_ld = (std::max(n, si_cap) + 2) & ~1;
+  vsz[V_SCRATCH] = std::max(std::max(8 * uv_ld, PQP_NW * 128), PQP_NW * (std::max(n, ne + d.ni) + 2));
+  vsz[V_RED] = PQP_NW * 16;
+  vsz[V_KT] = ne + d.ni + 2;
+  int off = 0;
+  for (int v = 0; v < V_COUNT; ++v) {
+    L.voff[v] = off;
+    off += (int)rnd(vsz[v]);
+  }
+  L.voff[V_RUP] = L.voff[V_SE] + ne;
+  L.voff[V_CDX] = L.voff[V_ADX] + ne;
+  L.vec_doubles = off;
+  L.scratch_doubles = vsz[V_SCRATCH];
+  L.si_cap = si_cap;
+  L.ctas_per_sm = ctas;
+  L.kind = 1;
+  const int ldn = (n + 1) & ~1, ldb = (ne + d.ni + 1) & ~1;
+  int64_t sz[PA_COUNT];
+  sz[PA_M1] = rnd((int64_t)n * ldn + 2);
+  sz[PA_AS] = rnd((int64_t)n * ldb + 2); // Bt
+  sz[PA_MS] = rnd(tile_doubles(si_cap));
+  sz[PA_G] = rnd((int64_t)cap * (cap + 1) / 2 + 2);
+  sz[PA_Y] = 2;
+  sz[PA_VEC] = L.vec_doubles;
+  const int64_t nlist = std::max(nc, cap);
+  L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);
+  const int64_t budget = budget_bytes - 1024 /*static shared memory*/ - L.smem_int_bytes;
+  int64_t smem_d = 0, ws_d = 0;
+  auto put = [&](int id, bool want_smem) {
+    if (want_smem && (smem_d + sz[id]) * 8 <= budget) {
+      L.in_smem[id] = 1;
+      L.off[id] = smem_d;
+      smem_d += sz[id];
+    } else {
+      L.in_smem[id] = 0;
+      L.off[id] = ws_d;
+      ws_d += sz[id];
+    }
+  };
+  put(PA_VEC, true);
+  put(PA_MS, true);
+  put(PA_M1, false);
+  put(PA_AS, false);
+  put(PA_G, false);
+  put(PA_Y, false);
+  L.smem_doubles = (int32_t)smem_d;
+  L.ws_doubles = std::max<int64_t>(ws_d, 2);
+  return (L.in_smem[PA_VEC] && L.in_smem[PA_MS]) ? 0 : 1;
+}
+
 int64_t
 sym_doubles(int64_t m)
 {
@@ -223,7 +307,28 @@ make_layout(pqp_batch* b)
   // generic fallback first (always valid as long as the vectors fit somewhere)
   fill_layout(d, b->lay_gen, max_smem, false, false, false, d.cap, 1);
   bool done = false;
-  if (m == "auto" || m == "compact") {
+  // tile layout (specialised kernel): dense Hessian, no box constraints, n even and <= 128
+  if ((m == "auto" || m == "tile") && d.hess == PQP_HESSIAN_DENSE && !d.box && (d.n % 2) == 0 && d.n <= 128 && d.n >= 2 && d.ne + d.ni <= 254 && d.nc > 0) {
+    const int64_t per_cta = ((int64_t)smem_sm - 2 * 1024) / 2;
+    int best = 0;
+    for (int cnd = std::min(std::max(d.cap, d.n), 128); cnd >= std::max(d.n, d.ne + 1); --cnd) { // P is inverted inside the S^-1 storage: cap >= n
+      PqpLayout probe;
+      if (fill_layout_tile(d, probe, per_cta, cnd, 2) == 0) {
+        best = cnd;
+        break;
+      }
+    }
+    if (const char* e = std::getenv("PQP_SI_CAP")) { // test hook: force a small capacity to exercise the retry path
+      int v = std::atoi(e);
+      if (v >= std::max(d.n, d.ne + 1) && v < best) best = v;
+    }
+    const int need = d.ne + std::min(d.nc, std::max(8, (d.nc + 1) / 2));
+    if (best >= std::min(d.cap, need)) {
+      fill_layout_tile(d, b->lay, per_cta, best, 2);
+      done = true;
+    }
+  }
+  if (!done && (m == "auto" || m == "compact")) {
     // two CTAs per SM: each gets half of the SM's shared memory minus the 1 KB system reserve
     const int64_t per_cta = ((int64_t)smem_sm - 2 * 1024) / 2;
     PqpLayout probe;

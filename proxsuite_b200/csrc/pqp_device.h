@@ -88,6 +88,7 @@ enum PqpVec {
   V_ALPHAS, V_GRADS,         // 2*nc + 2
   V_SCRATCH,                 // partial-sum scratch
   V_RED,                     // reduction scratch (64)
+  V_KT,                      // ne + ni products of one Bt pass (tile layout)
   V_COUNT
 };
 
@@ -103,6 +104,7 @@ struct PqpLayout
   int64_t ws_doubles;         // per-CTA global workspace in doubles
   int32_t si_cap;             // dual-block capacity of the S^-1 storage (<= dims.cap)
   int32_t ctas_per_sm;        // resident CTAs per SM this layout is sized for
+  int32_t kind;               // 0: packed layouts (pqp_solver_body.inl), 1: tile layout (pqp_fast_body.inl)
 };
 
 struct PqpSolveArgs

@@ -1,0 +1,1926 @@
+// Device code of the TILE kernel: the specialisation of the solve kernel for dense
+// Hessians without box constraints, n even and <= 128, dual block <= 128 (the
+// headline shapes). Same algorithm and driver as pqp_solver_body.inl; different
+// linear-algebra layer: every matrix-vector product is an AXPY-form streaming
+// pass (no cross-lane reductions), S^-1 lives in shared memory in 32 x 32 tile
+// storage, P^-1 / Bt / G in the per-CTA L2 workspace. See DESIGN.md section 3.
+
+
+struct Ctx
+{
+  int n, ne, ni, nc, box, hess, cap;
+  int ns; // current size of the dual block: ne + number of active inequalities
+  // factor storage
+  double *Pi, *As, *Si, *G, *Y;
+  double* Bt;      // [A_s; C_s]^T, n x ldb (L2 workspace)
+  double* kt;      // ne + ni products of one Bt pass (shared memory)
+  int ldb, ldn;    // leading dimensions of Bt and Pi (even)
+  const double *Hs, *Cs;        // scaled matrices of this QP (global)
+  const double *Hm, *Am, *Cm;   // model matrices (global, unscaled)
+  // vectors
+  double *x, *y, *z, *xp, *yp, *zp;
+  double *dx, *ds, *dz;
+  double *rx, *rs, *ex, *es;
+  double *dual, *se, *rup, *si;
+  double *hdx, *adx, *atdy, *cdx, *ctdz, *q;
+  double *gs, *bs, *us, *ls, *is, *delta;
+  double *b, *u, *l;
+  double *d1inv, *dsv, *dsinv;
+  double *t1, *t2, *t3, *s1, *s2, *s3, *s4;
+  double *alphas, *grads, *scratch, *red;
+  int *cons_slot, *slot_cons, *list1, *list2;
+  unsigned char *act_up, *act_low;
+  int *iscratch; // 2*NW + 8 ints
+  double c_scale; // ruiz.c
+  long long* prof; // per-phase cycle counters (shared memory) or NULL
+  int vec_smem;    // 1: the vector arena is in shared memory
+  int pi_smem;     // 1: P^-1 lives in shared memory (else global, read through L2)
+  int si_cap;      // largest dual-block size the S^-1 storage can hold
+  int uv_ld;       // leading dimension of the 8 sweep panel vectors kept in `scratch`
+  int overflow;    // set when an insertion would exceed si_cap (QP is retried by the generic kernel)
+};
+
+// local (register) copies of the vector pointers with the address-space hint
+#define PQP_VECS(c)   \
+  double* const v_x = c.x; PQP_SM(v_x); (void)v_x;   \
+  double* const v_y = c.y; PQP_SM(v_y); (void)v_y;   \
+  double* const v_z = c.z; PQP_SM(v_z); (void)v_z;   \
+  double* const v_xp = c.xp; PQP_SM(v_xp); (void)v_xp;   \
+  double* const v_yp = c.yp; PQP_SM(v_yp); (void)v_yp;   \
+  double* const v_zp = c.zp; PQP_SM(v_zp); (void)v_zp;   \
+  double* const v_dx = c.dx; PQP_SM(v_dx); (void)v_dx;   \
+  double* const v_ds = c.ds; PQP_SM(v_ds); (void)v_ds;   \
+  double* const v_dz = c.dz; PQP_SM(v_dz); (void)v_dz;   \
+  double* const v_rx = c.rx; PQP_SM(v_rx); (void)v_rx;   \
+  double* const v_rs = c.rs; PQP_SM(v_rs); (void)v_rs;   \
+  double* const v_ex = c.ex; PQP_SM(v_ex); (void)v_ex;   \
+  double* const v_es = c.es; PQP_SM(v_es); (void)v_es;   \
+  double* const v_dual = c.dual; PQP_SM(v_dual); (void)v_dual;   \
+  double* const v_se = c.se; PQP_SM(v_se); (void)v_se;   \
+  double* const v_rup = c.rup; PQP_SM(v_rup); (void)v_rup;   \
+  double* const v_si = c.si; PQP_SM(v_si); (void)v_si;   \
+  double* const v_hdx = c.hdx; PQP_SM(v_hdx); (void)v_hdx;   \
+  double* const v_adx = c.adx; PQP_SM(v_adx); (void)v_adx;   \
+  double* const v_atdy = c.atdy; PQP_SM(v_atdy); (void)v_atdy;   \
+  double* const v_cdx = c.cdx; PQP_SM(v_cdx); (void)v_cdx;   \
+  double* const v_ctdz = c.ctdz; PQP_SM(v_ctdz); (void)v_ctdz;   \
+  double* const v_q = c.q; PQP_SM(v_q); (void)v_q;   \
+  double* const v_gs = c.gs; PQP_SM(v_gs); (void)v_gs;   \
+  double* const v_bs = c.bs; PQP_SM(v_bs); (void)v_bs;   \
+  double* const v_us = c.us; PQP_SM(v_us); (void)v_us;   \
+  double* const v_ls = c.ls; PQP_SM(v_ls); (void)v_ls;   \
+  double* const v_is = c.is; PQP_SM(v_is); (void)v_is;   \
+  double* const v_delta = c.delta; PQP_SM(v_delta); (void)v_delta;   \
+  double* const v_b = c.b; PQP_SM(v_b); (void)v_b;   \
+  double* const v_u = c.u; PQP_SM(v_u); (void)v_u;   \
+  double* const v_l = c.l; PQP_SM(v_l); (void)v_l;   \
+  double* const v_d1inv = c.d1inv; PQP_SM(v_d1inv); (void)v_d1inv;   \
+  double* const v_t1 = c.t1; PQP_SM(v_t1); (void)v_t1;   \
+  double* const v_t2 = c.t2; PQP_SM(v_t2); (void)v_t2;   \
+  double* const v_t3 = c.t3; PQP_SM(v_t3); (void)v_t3;   \
+  double* const v_s1 = c.s1; PQP_SM(v_s1); (void)v_s1;   \
+  double* const v_s2 = c.s2; PQP_SM(v_s2); (void)v_s2;   \
+  double* const v_s3 = c.s3; PQP_SM(v_s3); (void)v_s3;   \
+  double* const v_s4 = c.s4; PQP_SM(v_s4); (void)v_s4;   \
+  double* const v_alphas = c.alphas; PQP_SM(v_alphas); (void)v_alphas;   \
+  double* const v_grads = c.grads; PQP_SM(v_grads); (void)v_grads;   \
+  double* const v_scratch = c.scratch; PQP_SM(v_scratch); (void)v_scratch;   \
+  double* const v_red = c.red; PQP_SM(v_red); (void)v_red;   \
+  (void)0
+
+__device__ __forceinline__ double nanmax(double a, double b)
+{
+  return (b > a || b != b) ? b : a;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// K sums followed by KM maxima reduced over the CTA; the result is returned to
+// every thread (block-uniform control flow depends on it).
+template<int KS, int KM>
+__device__ void block_reduce(const Ctx& c, double* sums, double* maxs)
+{
+  PQP_VECS(c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) sums[k] = warp_sum(sums[k]);
+#pragma unroll
+  for (int k = 0; k < KM; ++k) maxs[k] = warp_max(maxs[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < KS; ++k) v_red[warp * (KS + KM) + k] = sums[k];
+#pragma unroll
+    for (int k = 0; k < KM; ++k) v_red[warp * (KS + KM) + KS + k] = maxs[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += v_red[w * (KS + KM) + k];
+    sums[k] = s;
+  }
+#pragma unroll
+  for (int k = 0; k < KM; ++k) {
+    double m = v_red[KS + k];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = nanmax(m, v_red[w * (KS + KM) + KS + k]);
+    maxs[k] = m;
+  }
+  __syncthreads();
+}
+__device__ double block_max1(const Ctx& c, double v)
+{
+  double dummy[1] = { 0 };
+  double m[1] = { v };
+  block_reduce<0, 1>(c, dummy, m);
+  return m[0];
+}
+__device__ double block_sum1(const Ctx& c, double v)
+{
+  double s[1] = { v };
+  double dummy[1] = { 0 };
+  block_reduce<1, 0>(c, s, dummy);
+  return s[0];
+}
+
+// inclusive prefix sum over elements 0..cnt-1 (one per thread, cnt <= NT)
+__device__ double block_scan_incl(const Ctx& c, double v)
+{
+  PQP_VECS(c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(FULL, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) v_red[warp] = v;
+  __syncthreads();
+  double off = 0;
+  for (int w = 0; w < warp; ++w) off += v_red[w];
+  __syncthreads();
+  return v + off;
+}
+
+// ordered stream compaction: list[k] = indices i in [0, count) with pred(i),
+// ascending. Returns the number of entries (block-uniform).
+template<class Pred>
+__device__ int block_compact(const Ctx& c, int count, int* list, Pred pred)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int base = 0;
+  for (int i0 = 0; i0 < count; i0 += NT) {
+    int i = i0 + threadIdx.x;
+    bool p = (i < count) && pred(i);
+    unsigned m = __ballot_sync(FULL, p);
+    if (lane == 0) c.iscratch[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += c.iscratch[w];
+    int tot = 0;
+    for (int w = 0; w < NW; ++w) tot += c.iscratch[w];
+    if (p) list[off + __popc(m & ((1u << lane) - 1u))] = i;
+    base += tot;
+    __syncthreads();
+  }
+  return base;
+}
+
+__device__ __forceinline__ int sym_off(int i)
+{
+  return (i * (i + 1)) >> 1; // packed lower WITH diagonal: row i has i+1 entries
+}
+__device__ __forceinline__ size_t gidx(int a, int b)
+{
+  int hi = a > b ? a : b, lo = a > b ? b : a;
+  return (size_t)hi * (size_t)(hi + 1) / 2 + (size_t)lo;
+}
+
+// Reduce RR per-row partial sums across the 32 lanes with 1 + log2 steps per
+// group instead of 5 shuffles per row. On return lane (32/RR)*r holds the sum
+// of row r in d[0].
+template<int RR>
+__device__ __forceinline__ void reduce_rows(double (&d)[RR], int lane)
+{
+  int width = 16;
+#pragma unroll
+  for (int cnt = RR; cnt > 1; cnt >>= 1) {
+    const bool hi = (lane & width) != 0;
+#pragma unroll
+    for (int k = 0; k < cnt / 2; ++k) {
+      const double send = hi ? d[k] : d[k + cnt / 2];
+      const double keep = hi ? d[k + cnt / 2] : d[k];
+      d[k] = keep + __shfl_xor_sync(FULL, send, width);
+    }
+    width >>= 1;
+  }
+  for (; width >= 1; width >>= 1) d[0] += __shfl_xor_sync(FULL, d[0], width);
+}
+
+#define RPB (32 / NW) // rows per warp per 32-row tile
+
+// ---------------------------------------------------------------------------
+// AXPY-form streaming pass (the only matrix-vector primitive of this kernel):
+//   out[j] = add[j] + sign * sum_{k < nrows} coef[ck] * row_k[j],   j < ncols
+// row_k = base0 + k*ld for k < split, else base1 + list[k]*ld (list == null:
+// base1 + (k - split)*ld); ck = k, or list[k] when byid. Warp w owns rows
+// w, w+NW, ...; a lane owns column PAIRS (16-byte loads, no shuffles, no
+// per-row predicates); the NW partial vectors are combined through shared
+// memory. Every product of the iteration is put in this form by keeping the
+// transposed copy Bt = [A_s; C_s]^T next to the row-major matrices and by
+// using the symmetry of H_s and P^-1. Rows must be 16-byte aligned (ld even).
+// ---------------------------------------------------------------------------
+template<int NCH>
+__device__ void axpy_pass_t(const Ctx& c, const double* __restrict__ base0, int split, const double* __restrict__ base1, int ld, const int* __restrict__ list, int byid, int nrows, const double* __restrict__ coef, int ncols, double* out, const double* add, double sign)
+{
+  constexpr int UNR = (NCH <= 2) ? 4 : 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* const scr = c.scratch;
+  PQP_SM(scr);
+  PQP_SM(coef);
+  PQP_SM(out);
+  const int np = (ncols + 1) >> 1;
+  bool pv[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) pv[ch] = lane + 32 * ch < np;
+  double2 acc[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) acc[ch] = make_double2(0.0, 0.0);
+  auto rowptr = [&](int k, double& cf) -> const double2* {
+    int id = k;
+    const double* b = base0;
+    if (k >= split) {
+      b = base1;
+      id = list ? list[k] : k - split;
+    }
+    cf = coef[(byid && k >= split) ? id : k];
+    return reinterpret_cast<const double2*>(b + (size_t)id * (size_t)ld) + lane;
+  };
+  int k = warp;
+  _Pragma("unroll 1") for (; k + (UNR - 1) * NW < nrows; k += UNR * NW) {
+    const double2* rp[UNR];
+    double cf[UNR];
+    double2 v[UNR][NCH];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) rp[u] = rowptr(k + u * NW, cf[u]);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) v[u][ch] = pv[ch] ? rp[u][32 * ch] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        acc[ch].x = fma(cf[u], v[u][ch].x, acc[ch].x);
+        acc[ch].y = fma(cf[u], v[u][ch].y, acc[ch].y);
+      }
+    }
+  }
+  _Pragma("unroll 1") for (; k < nrows; k += NW) {
+    double cf;
+    const double2* rp = rowptr(k, cf);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (pv[ch]) {
+        const double2 v = rp[32 * ch];
+        acc[ch].x = fma(cf, v.x, acc[ch].x);
+        acc[ch].y = fma(cf, v.y, acc[ch].y);
+      }
+    }
+  }
+  double2* const scr2 = reinterpret_cast<double2*>(scr);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    if (pv[ch]) scr2[warp * np + lane + 32 * ch] = acc[ch];
+  }
+  __syncthreads();
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < ncols; j += NT) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += scr[w * 2 * np + j];
+    out[j] = (add ? add[j] : 0.0) + sign * s;
+  }
+  __syncthreads();
+}
+
+__device__ __noinline__ void axpy_pass2(const Ctx& c, const double* base0, int split, const double* base1, int ld, const int* list, int byid, int nrows, const double* coef, int ncols, double* out, const double* add, double sign)
+{
+  const int np = (ncols + 1) >> 1;
+  if (np <= 32)
+    axpy_pass_t<1>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign);
+  else if (np <= 64)
+    axpy_pass_t<2>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign);
+  else if (np <= 96)
+    axpy_pass_t<3>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign);
+  else
+    axpy_pass_t<4>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign);
+}
+// all rows from one matrix
+__device__ __forceinline__ void axpy_pass(const Ctx& c, const double* base, int ld, int nrows, const double* coef, int ncols, double* out, const double* add, double sign)
+{
+  axpy_pass2(c, base, nrows, base, ld, nullptr, 0, nrows, coef, ncols, out, add, sign);
+}
+
+// ---------------------------------------------------------------------------
+// Symmetric matrices in TILE storage (S^-1, and P during its inversion).
+// The lower triangle is cut into 32 x 32 tiles (bi, bj), bj <= bi, each stored
+// row-major with a row stride of 33 doubles, so that a warp can read a tile by
+// rows (lanes = columns) AND by columns (lanes = rows) without bank conflicts.
+// Diagonal tiles hold both halves. With this, y = T x needs no cross-lane
+// reduction: an off-diagonal tile contributes T x_j to y_i through the column
+// reading and T^T x_i to y_j through the row reading, both accumulating into
+// lane-stationary registers; rank-k updates touch every stored element once.
+// Entries outside the live order are kept at zero. Block row bi holds
+// min(32, cap - 32 bi) rows; cap <= 128.
+// ---------------------------------------------------------------------------
+#define TS_LD 33
+#define TS_TILE (32 * TS_LD)
+__device__ __forceinline__ int ts_rows(int cap, int bi)
+{
+  return min(32, cap - 32 * bi);
+}
+__device__ __forceinline__ int ts_tile(int cap, int bi, int bj)
+{
+  return ((bi * (bi + 1)) >> 1) * TS_TILE + bj * ts_rows(cap, bi) * TS_LD;
+}
+// position of (i, j); valid for j's block <= i's block
+__device__ __forceinline__ int ts_idx(int cap, int i, int j)
+{
+  return ts_tile(cap, i >> 5, j >> 5) + (i & 31) * TS_LD + (j & 31);
+}
+__device__ __forceinline__ double ts_get(const double* T, int cap, int i, int j)
+{
+  return (i >= j) ? T[ts_idx(cap, i, j)] : T[ts_idx(cap, j, i)];
+}
+// store (i, j) = (j, i) = v
+__device__ __forceinline__ void ts_put(double* T, int cap, int i, int j, double v)
+{
+  const int hi = i >= j ? i : j, lo = i >= j ? j : i;
+  T[ts_idx(cap, hi, lo)] = v;
+  if ((hi >> 5) == (lo >> 5) && hi != lo) T[ts_idx(cap, lo, hi)] = v;
+}
+// doubles covered by the block rows holding order n
+__device__ __forceinline__ int ts_extent(int cap, int n)
+{
+  const int nb = (n + 31) >> 5;
+  return nb == 0 ? 0 : ts_tile(cap, nb - 1, 0) + nb * ts_rows(cap, nb - 1) * TS_LD;
+}
+
+// y = T x (order n). x and y must not alias. Uses c.scratch (NW x 128).
+__device__ __noinline__ void tsym_mv(const Ctx& c, const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cap = c.si_cap;
+  double* const scr = c.scratch;
+  PQP_SM(T);
+  PQP_SM(x);
+  PQP_SM(y);
+  PQP_SM(scr);
+  const int nb = (n + 31) >> 5;
+  const int r0 = RPB * warp; // this warp's rows (row reading) / columns (column reading) inside every tile
+  double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+  double xr[4][RPB];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+#pragma unroll
+    for (int r = 0; r < RPB; ++r) {
+      const int i = 32 * b + r0 + r;
+      xr[b][r] = (i < n) ? x[i] : 0.0;
+    }
+  }
+#pragma unroll
+  for (int bi = 0; bi < 4; ++bi) {
+    if (bi < nb) {
+      const int rows = min(32, n - 32 * bi); // live rows of this block
+#pragma unroll
+      for (int bj = 0; bj <= bi; ++bj) {
+        const double* tile = T + ts_tile(cap, bi, bj);
+        if (r0 < rows) {
+#pragma unroll
+          for (int r = 0; r < RPB; ++r) {
+            if (r0 + r < rows) acc[bj] = fma(tile[(r0 + r) * TS_LD + lane], xr[bi][r], acc[bj]);
+          }
+        }
+        if (bj < bi && lane < rows) {
+#pragma unroll
+          for (int q = 0; q < RPB; ++q) acc[bi] = fma(tile[lane * TS_LD + r0 + q], xr[bj][q], acc[bi]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    if (b < nb) scr[warp * 128 + 32 * b + lane] = acc[b];
+  }
+  __syncthreads();
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += scr[w * 128 + j];
+    y[j] = s;
+  }
+  __syncthreads();
+}
+
+// T[i][j] += u_i v_j on every stored element with i, j < n (u, v in shared memory)
+__device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, const double* __restrict__ u, const double* __restrict__ v, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cap = c.si_cap;
+  PQP_SM(T);
+  PQP_SM(u);
+  PQP_SM(v);
+  const int nb = (n + 31) >> 5;
+  const int r0 = RPB * warp;
+  double vl[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int j = 32 * b + lane;
+    vl[b] = (j < n) ? v[j] : 0.0;
+  }
+#pragma unroll
+  for (int bi = 0; bi < 4; ++bi) {
+    if (bi < nb) {
+      const int rows = min(32, n - 32 * bi);
+      if (r0 < rows) {
+        double ur[RPB];
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) {
+          const int i = 32 * bi + r0 + r;
+          ur[r] = (i < n) ? u[i] : 0.0;
+        }
+#pragma unroll
+        for (int bj = 0; bj <= bi; ++bj) {
+          double* tile = T + ts_tile(cap, bi, bj);
+          double a[RPB];
+#pragma unroll
+          for (int r = 0; r < RPB; ++r) a[r] = (r0 + r < rows) ? tile[(r0 + r) * TS_LD + lane] : 0.0;
+#pragma unroll
+          for (int r = 0; r < RPB; ++r) {
+            if (r0 + r < rows) tile[(r0 + r) * TS_LD + lane] = fma(ur[r], vl[bj], a[r]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// T[i][j] += sum_k U[i][k] V[k][j], k = 0..3 in order. U is stored row-interleaved
+// (4 doubles per row i), V as four vectors of stride ldv.
+__device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cap = c.si_cap;
+  PQP_SM(T);
+  PQP_SM(U);
+  PQP_SM(V);
+  const int nb = (n + 31) >> 5;
+  const int r0 = RPB * warp;
+  double vl[4][4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int j = 32 * b + lane;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) vl[k][b] = (j < n) ? V[k * ldv + j] : 0.0;
+  }
+#pragma unroll
+  for (int bi = 0; bi < 4; ++bi) {
+    if (bi < nb) {
+      const int rows = min(32, n - 32 * bi);
+      if (r0 < rows) {
+#pragma unroll
+        for (int r = 0; r < RPB; ++r) {
+          if (r0 + r < rows) {
+            const int i = 32 * bi + r0 + r;
+            const double2 ua = reinterpret_cast<const double2*>(U)[2 * i];
+            const double2 ub = reinterpret_cast<const double2*>(U)[2 * i + 1];
+            double a[4];
+#pragma unroll
+            for (int bj = 0; bj <= bi; ++bj) a[bj] = T[ts_tile(cap, bi, bj) + (r0 + r) * TS_LD + lane];
+#pragma unroll
+            for (int bj = 0; bj <= bi; ++bj) T[ts_tile(cap, bi, bj) + (r0 + r) * TS_LD + lane] = fma(ub.y, vl[3][bj], fma(ub.x, vl[2][bj], fma(ua.y, vl[1][bj], fma(ua.x, vl[0][bj], a[bj]))));
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// In-place inverse of the SPD matrix held in tile storage by BLOCKED symmetric
+// Gauss-Jordan sweeps (Goodnight's sweep operator, four pivots per pass).
+// One scalar sweep on pivot k maps
+//   T_kk -> -1/d,  T_kj -> T_kj/d,  T_ij -> T_ij - T_ik T_kj / d   (d = T_kk).
+// Four consecutive sweeps touch an entry outside the pivot rows/columns K only
+// through  T_ij += sum_{k in K} U_ik V_kj,  U_ik = T^(k)_ik (column k just
+// before its own sweep), V_kj = -U_jk / d_k, and U^(k) depends only on row i of
+// the n x 4 panel T[:, K] plus the 4 x 4 pivot block. Every thread sweeps its
+// own panel row in registers (the pivot block is swept redundantly by all),
+// writes the finished K rows/columns back, stores U, V (zero on K), and one
+// rank-4 pass applies the rest with the FMA chain the scalar sweeps would have
+// used. After all blocks the array holds -T^-1. Requires n <= NT.
+// `uv`: 8 * ldv doubles. Replaces Ldlt::factorize for the blocks this path
+// inverts (linalg/dense/ldlt.hpp:718-744, factorize.hpp:91-148).
+__device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict__ T, double* __restrict__ uv, int ldv, int n)
+{
+  PQP_SM(T);
+  PQP_SM(uv);
+  const int cap = c.si_cap;
+  double* const U = uv;           // [n][4]
+  double* const V = uv + 4 * ldv; // [4][ldv]
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    const int kb = min(4, n - k0);
+    double a[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[q][r] = (q < kb && r < kb) ? ts_get(T, cap, k0 + q, k0 + r) : ((q == r) ? 1.0 : 0.0);
+    }
+    const int i = threadIdx.x;
+    double p[4], ui[4], vi[4];
+    const int ai = i - k0; // position of this row inside the pivot block when 0 <= ai < kb
+    const bool inK = (ai >= 0) && (ai < kb);
+    if (i < n) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) p[l] = (l < kb) ? ts_get(T, cap, i, k0 + l) : 0.0;
+    }
+    __syncthreads(); // every thread holds the pivot block and its panel row before anything is overwritten
+    if (i < n) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < kb) {
+          const double inv = 1.0 / a[k][k];
+          double vK[4];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) vK[l] = -a[k][l] * inv;
+          const double pk = p[k];
+          if (ai == k) {
+            ui[k] = 0.0;
+            vi[k] = 0.0;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? -inv : p[l] * inv;
+          } else {
+            ui[k] = inK ? 0.0 : pk;
+            vi[k] = inK ? 0.0 : -pk * inv;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? pk * inv : fma(pk, vK[l], p[l]);
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (m != k) {
+              const double amk = a[m][k];
+#pragma unroll
+              for (int l = 0; l < 4; ++l) a[m][l] = (l == k) ? amk * inv : fma(amk, vK[l], a[m][l]);
+            }
+          }
+#pragma unroll
+          for (int l = 0; l < 4; ++l) a[k][l] = (l == k) ? -inv : a[k][l] * inv;
+        } else {
+          ui[k] = 0.0;
+          vi[k] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int col = k0 + l;
+        if (l < kb && (i >= col || !inK)) ts_put(T, cap, i, col, p[l]);
+        V[l * ldv + i] = vi[l];
+      }
+      reinterpret_cast<double2*>(U)[2 * i] = make_double2(ui[0], ui[1]);
+      reinterpret_cast<double2*>(U)[2 * i + 1] = make_double2(ui[2], ui[3]);
+    }
+    __syncthreads();
+    tsym_rank4(c, T, U, V, ldv, n);
+  }
+  const int tot = ts_extent(cap, n);
+  _Pragma("unroll 1") for (int e = threadIdx.x; e < tot; e += NT) T[e] = -T[e];
+  __syncthreads();
+}
+
+__device__ __forceinline__ int row_id(const Ctx& c, int s)
+{
+  return s < c.ne ? s : c.ne + c.slot_cons[s];
+}
+
+// y = P^-1 v  (Pi = P^-1 explicit, full square n x ldn in the L2 workspace)
+__device__ __forceinline__ void apply_Pinv(const Ctx& c, const double* v, double* y)
+{
+  axpy_pass(c, c.Pi, c.ldn, c.n, v, c.n, y, nullptr, 1.0);
+}
+
+// Solve K [ox; os] = [b1; b2],  K = [P B^T; B -Dlt], with the explicit block
+// inverses:  t = P^-1 b1;  lam = S^-1 (B t - b2);  x = P^-1 (b1 - B^T lam).
+// In place allowed (ox == b1, os == b2). Replaces Ldlt::solve_in_place
+// (ldlt.hpp:767-782).
+__device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const double* b2, double* ox, double* os)
+{
+  PQP_VECS(c);
+  const int ns = c.ns, n = c.n, ne = c.ne;
+  if (ns == 0) {
+    apply_Pinv(c, b1, v_t1);
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) ox[j] = v_t1[j];
+    __syncthreads();
+    return;
+  }
+  apply_Pinv(c, b1, v_t1);
+  // B t for every row of [A_s; C_s] at once (Bt = B^T), then pick the slots
+  axpy_pass(c, c.Bt, c.ldb, n, v_t1, ne + c.ni, c.kt, nullptr, 1.0);
+  _Pragma("unroll 1") for (int s = threadIdx.x; s < ns; s += NT) v_s1[s] = c.kt[row_id(c, s)] - b2[s];
+  __syncthreads();
+  tsym_mv(c, c.Si, v_s1, os, ns);
+  // t2 = b1 - B^T lam : equality rows, then the active rows of C_s
+  axpy_pass2(c, c.As, ne, c.Cs, n, c.slot_cons, 0, ns, os, n, v_t2, b1, -1.0);
+  apply_Pinv(c, v_t2, ox);
+}
+
+// Gram row of dual slot s against slots 0..s:  y = P^-1 b_s (-> t1),
+// s3[j] = b_j . y, stored in G by row id.
+__device__ void gram_row(Ctx& c, int s)
+{
+  PQP_VECS(c);
+  const int n = c.n, ne = c.ne;
+  const double* row = (s < ne) ? c.As + (size_t)s * n : c.Cs + (size_t)c.slot_cons[s] * n;
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) v_t2[j] = row[j];
+  __syncthreads();
+  apply_Pinv(c, v_t2, v_t1);
+  axpy_pass(c, c.Bt, c.ldb, n, v_t1, ne + c.ni, c.kt, nullptr, 1.0);
+  const int ids = row_id(c, s);
+  _Pragma("unroll 1") for (int j = threadIdx.x; j <= s; j += NT) {
+    const double g = c.kt[row_id(c, j)];
+    v_s3[j] = g;
+    c.G[gidx(ids, row_id(c, j))] = g;
+  }
+  __syncthreads();
+}
+
+// Append dual slot s == c.ns (already registered in slot_cons) with proximal
+// parameter mu: bordering of the explicit inverse
+//   w = S^-1 g, delta = (b.P^-1 b + mu) - g.w,
+//   S^-1 <- [S^-1 + w w^T/delta, -w/delta; -w^T/delta, 1/delta].
+// Replaces Ldlt::insert_block_at (ldlt.hpp:431-475, modify.hpp:131-264).
+__device__ __noinline__ void insert_slot(Ctx& c, double mu)
+{
+  PQP_VECS(c);
+  const int s = c.ns;
+  const int cap = c.si_cap;
+  if (s + 1 > cap) { // does not fit the shared-memory S^-1: hand the QP to the generic kernel
+    if (threadIdx.x == 0) c.overflow = 1;
+    __syncthreads();
+    return;
+  }
+  gram_row(c, s);
+  double delta = v_s3[s] + mu;
+  if (s > 0) {
+    tsym_mv(c, c.Si, v_s3, v_s1, s);
+    double part = 0;
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) part += v_s3[j] * v_s1[j];
+    delta -= block_sum1(c, part);
+    const double dinv = 1.0 / delta;
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) {
+      const double wj = v_s1[j] * dinv;
+      v_s2[j] = wj;
+      ts_put(c.Si, cap, s, j, -wj);
+    }
+    __syncthreads();
+    tsym_rank1(c, c.Si, v_s1, v_s2, s);
+  }
+  if (threadIdx.x == 0) {
+    c.Si[ts_idx(cap, s, s)] = 1.0 / delta;
+    c.ns = s + 1;
+  }
+  __syncthreads();
+}
+
+// Remove dual slot k (k >= ne): Schur complement of the explicit inverse,
+//   S'^-1 = T - q q^T / T_kk   (T = S^-1 without row/column k, q = column k),
+// then the last slot takes the place of k (slot order carries no meaning).
+// Replaces Ldlt::delete_at (ldlt.hpp:340-387).
+__device__ __noinline__ void delete_slot(Ctx& c, int k)
+{
+  PQP_VECS(c);
+  const int ns = c.ns, cap = c.si_cap, L = ns - 1;
+  double* T = c.Si;
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = ts_get(T, cap, i, k);
+  __syncthreads();
+  const double sinv = -1.0 / v_s1[k];
+  __syncthreads();
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
+    const double q = (i == k) ? 0.0 : v_s1[i]; // row / column k are dropped below
+    v_s2[i] = q;
+    v_s3[i] = q * sinv;
+  }
+  __syncthreads();
+  tsym_rank1(c, T, v_s2, v_s3, ns);
+  // move row / column L into k, clear row / column L
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = ts_get(T, cap, i, L);
+  __syncthreads();
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
+    if (k != L) {
+      if (i == k)
+        T[ts_idx(cap, k, k)] = v_s1[L];
+      else if (i != L)
+        ts_put(T, cap, i, k, v_s1[i]);
+    }
+    ts_put(T, cap, L, i, 0.0);
+  }
+  if (threadIdx.x == 0) {
+    const int cons_k = c.slot_cons[k], cons_L = c.slot_cons[L];
+    if (k != L) {
+      c.slot_cons[k] = cons_L;
+      c.cons_slot[cons_L] = k;
+    }
+    c.cons_slot[cons_k] = -1;
+    c.ns = L;
+  }
+  __syncthreads();
+}
+
+// S^-1 from the cached Gram matrix with the given proximal parameters
+// (S = Dlt + G): gather + sweep inversion. Replaces
+// Ldlt::diagonal_update_clobber_indices (ldlt.hpp:516-570) used by mu_update
+// (solver.hpp:130-169).
+__device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_in)
+{
+  PQP_VECS(c);
+  const int ns = c.ns, cap = c.si_cap;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = (ns + 31) >> 5;
+  for (int bi = 0; bi < nb; ++bi) {
+    const int rst = ts_rows(cap, bi);
+    for (int r = warp; r < rst; r += NW) {
+      const int s = 32 * bi + r;
+      const int ids = (s < ns) ? row_id(c, s) : 0;
+      for (int bj = 0; bj <= bi; ++bj) {
+        const int t = 32 * bj + lane;
+        double v = 0.0;
+        if (s < ns && t < ns) v = c.G[gidx(ids, row_id(c, t))] + ((t == s) ? (s < c.ne ? mu_eq : mu_in) : 0.0);
+        c.Si[ts_tile(cap, bi, bj) + r * TS_LD + lane] = v;
+      }
+    }
+  }
+  __syncthreads();
+  tsym_sweep_invert(c, c.Si, v_scratch, c.uv_ld, ns);
+}
+
+// P^-1 = (Hs + rho I)^-1, explicit: swept in the (free) S^-1 tile storage, then
+// written to the L2 workspace as a full square for the AXPY passes. Replaces
+// the x-block part of Ldlt::factorize (ldlt.hpp:718-744).
+__device__ __noinline__ void build_Pi(Ctx& c, double rho)
+{
+  PQP_VECS(c);
+  const int n = c.n, cap = c.si_cap;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = (n + 31) >> 5;
+  double* const work = c.Si;
+  for (int bi = 0; bi < nb; ++bi) {
+    const int rst = ts_rows(cap, bi);
+    for (int r = warp; r < rst; r += NW) {
+      const int i = 32 * bi + r;
+      for (int bj = 0; bj <= bi; ++bj) {
+        const int j = 32 * bj + lane;
+        double v = 0.0;
+        if (i < n && j < n) v = c.Hs[(size_t)i * n + j] + ((j == i) ? rho : 0.0);
+        work[ts_tile(cap, bi, bj) + r * TS_LD + lane] = v;
+      }
+    }
+  }
+  __syncthreads();
+  tsym_sweep_invert(c, work, v_scratch, c.uv_ld, n);
+  for (int i = warp; i < n; i += NW) {
+    for (int j = lane; j < c.ldn; j += 32) c.Pi[(size_t)i * c.ldn + j] = (j < n) ? ts_get(work, cap, i, j) : 0.0;
+  }
+  // leave the whole region clean for S^-1 (entries outside the live order must be zero)
+  const int tot = ts_extent(cap, cap);
+  __syncthreads();
+  _Pragma("unroll 1") for (int e = threadIdx.x; e < tot; e += NT) work[e] = 0.0;
+  __syncthreads();
+}
+
+// Bt = [A_s; C_s]^T (n x ldb) in the L2 workspace
+__device__ __noinline__ void build_Bt(Ctx& c)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = c.n, ne = c.ne, nr = c.ne + c.ni;
+  for (int r = warp; r < nr; r += NW) {
+    const double* row = (r < ne) ? c.As + (size_t)r * n : c.Cs + (size_t)(r - ne) * n;
+    for (int j = lane; j < n; j += 32) c.Bt[(size_t)j * c.ldb + r] = row[j];
+  }
+  if (c.ldb > nr) {
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) c.Bt[(size_t)j * c.ldb + nr] = 0.0;
+  }
+  __syncthreads();
+}
+
+// (Re)build the dual block for the slots 0..ns_target-1 currently registered:
+// Gram rows, then one sweep inversion. Used for the first factorisation
+// (equality rows only, helpers.hpp:241-285) and by refactorize (solver.hpp:40-87).
+__device__ __noinline__ void build_dual_block(Ctx& c, int ns_target, double mu_eq, double mu_in)
+{
+  for (int s = 0; s < ns_target; ++s) gram_row(c, s);
+  if (threadIdx.x == 0) c.ns = ns_target;
+  __syncthreads();
+  if (ns_target > 0) rebuild_Si_from_G(c, mu_eq, mu_in);
+}
+
+// optional per-phase cycle accounting (thread 0 only; enabled when args.prof != NULL)
+enum ProfPhase { PH_STAGE = 0, PH_M1, PH_EQ, PH_INSERT, PH_DELETE, PH_SOLVE, PH_RESID, PH_LS, PH_MU, PH_GLOBAL, PH_NEWTON_MISC, PH_TOTAL, PH_COUNT };
+#define PROF_T0() (c.prof ? clock64() : 0ll)
+#define PROF_ADD(ph, t0)                                                                                                                                                                                                                                       \
+  do {                                                                                                                                                                                                                                                         \
+    if (c.prof && threadIdx.x == 0) c.prof[ph] += clock64() - (t0);                                                                                                                                                                                           \
+  } while (0)
+
+struct Scal
+{
+  double rho, mu_eq, mu_in, mu_eq_inv, mu_in_inv, nu;
+  long long iter, iter_ext, mu_updates;
+  int status;
+  double iterative_residual;
+  bool factor_fresh; // !constraints_changed (solver.hpp:48)
+};
+
+// err = rhs - K dw, with the by-products the Newton loop reuses
+// (solver.hpp:245-318; quirk 3 of SURVEY Appendix A). Returns |err|_inf.
+__device__ __noinline__ double kkt_residual(const Ctx& c, const Scal& sc)
+{
+  PQP_VECS(c);
+  const int n = c.n, ne = c.ne, ns = c.ns;
+  axpy_pass(c, c.Hs, n, n, v_dx, n, v_hdx, nullptr, 1.0);                    // H dx (H symmetric)
+  axpy_pass(c, c.Bt, c.ldb, n, v_dx, ne + c.ni, v_adx, nullptr, 1.0);        // [A dx; C dx] (adx, cdx contiguous)
+  axpy_pass2(c, c.As, ne, c.Cs, n, c.slot_cons, 0, ns, v_ds, n, v_atdy, nullptr, 1.0); // A^T dy + C_J^T dz_J
+  double m = 0;
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
+    double e = v_rx[j] - (v_hdx[j] + sc.rho * v_dx[j] + v_atdy[j]); // atdy = A^T dy + C_J^T dz_J
+    v_ex[j] = e;
+    m = nanmax(m, fabs(e));
+  }
+  _Pragma("unroll 1") for (int s = threadIdx.x; s < ns; s += NT) {
+    double e;
+    if (s < ne)
+      e = v_rs[s] - (v_adx[s] - sc.mu_eq * v_ds[s]);
+    else
+      e = v_rs[s] - (v_cdx[c.slot_cons[s]] - sc.mu_in * v_ds[s]);
+    v_es[s] = e;
+    m = nanmax(m, fabs(e));
+  }
+  return block_max1(c, m);
+}
+
+// solver.hpp:40-87: rebuild everything from scratch (same active set)
+__device__ void refactorize(Ctx& c, Scal& sc)
+{
+  if (sc.factor_fresh) return;
+  const int ns_target = c.ns;
+  __syncthreads();
+  build_Pi(c, sc.rho);
+  build_dual_block(c, ns_target, sc.mu_eq, sc.mu_in);
+  sc.factor_fresh = true;
+}
+
+// solver.hpp:408-541
+__device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_settings& S, double eps)
+{
+  PQP_VECS(c);
+  for (int pass = 0; pass < 2; ++pass) {
+    int it = 0, it_stab = 0;
+    long long tp = PROF_T0();
+    solve_kkt(c, v_rx, v_rs, v_dx, v_ds);
+    PROF_ADD(PH_SOLVE, tp);
+    tp = PROF_T0();
+    double err = kkt_residual(c, sc);
+    PROF_ADD(PH_RESID, tp);
+    ++it;
+    double prev = err;
+    while (err >= eps) {
+      if (it >= S.nb_iterative_refinement) break;
+      ++it;
+      tp = PROF_T0();
+      solve_kkt(c, v_ex, v_es, v_ex, v_es);
+      _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) v_dx[j] += v_ex[j];
+      _Pragma("unroll 1") for (int s = threadIdx.x; s < c.ns; s += NT) v_ds[s] += v_es[s];
+      __syncthreads();
+      PROF_ADD(PH_SOLVE, tp);
+      tp = PROF_T0();
+      err = kkt_residual(c, sc);
+      PROF_ADD(PH_RESID, tp);
+      if (err > prev)
+        it_stab += 1;
+      else
+        it_stab = 0;
+      if (it_stab == 2) break;
+      prev = err;
+    }
+    sc.iterative_residual = err;
+    if (pass == 0 && err >= fmax(eps, S.eps_refact) && !sc.factor_fresh) {
+      refactorize(c, sc);
+      continue;
+    }
+    break;
+  }
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) v_rx[j] = 0;
+  _Pragma("unroll 1") for (int s = threadIdx.x; s < c.cap; s += NT) v_rs[s] = 0;
+  __syncthreads();
+}
+
+// linesearch.hpp:551-786 with act[i] = act_up | act_low
+__device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
+{
+  // deletions, from the last slot to the first
+  int ndel = block_compact(c, c.ns - c.ne, c.list1, [&](int k) {
+    int cons = c.slot_cons[c.ne + k];
+    return !(c.act_up[cons] || c.act_low[cons]);
+  });
+  long long tp = PROF_T0();
+  for (int k = ndel - 1; k >= 0; --k) delete_slot(c, c.ne + c.list1[k]);
+  PROF_ADD(PH_DELETE, tp);
+  tp = PROF_T0();
+  int nadd = block_compact(c, c.nc, c.list1, [&](int i) { return (c.act_up[i] || c.act_low[i]) && c.cons_slot[i] < 0; });
+  for (int k = 0; k < nadd; ++k) {
+    if (threadIdx.x == 0) {
+      int cons = c.list1[k];
+      c.slot_cons[c.ns] = cons;
+      c.cons_slot[cons] = c.ns;
+    }
+    __syncthreads();
+    insert_slot(c, sc.mu_in);
+  }
+  PROF_ADD(PH_INSERT, tp);
+  if (ndel > 0 || nadd > 0) sc.factor_fresh = false;
+}
+
+// unscaled global residual pieces -------------------------------------------------
+struct Glob
+{
+  double pri_lhs, pri_eq_rhs0, pri_in_rhs0, pri_eq_lhs, pri_in_lhs;
+  double dua_lhs, dua_rhs0, dua_rhs1, dua_rhs3, gap, rhs_gap;
+};
+
+// utils.hpp:166-252
+// Streaming passes shared by the global residuals: H x -> t1, A x -> se,
+// A^T y -> t2, C x -> rup, C^T z_C -> t3 (one pass per matrix).
+__device__ __noinline__ void global_passes(Ctx& c, bool primal, bool dual)
+{
+  PQP_VECS(c);
+  const int n = c.n, ne = c.ne, ni = c.ni;
+  if (dual) {
+    axpy_pass(c, c.Hs, n, n, v_x, n, v_t1, nullptr, 1.0);
+    axpy_pass(c, c.As, n, ne, v_y, n, v_t2, nullptr, 1.0);
+    axpy_pass(c, c.Cs, n, ni, v_z, n, v_t3, nullptr, 1.0);
+  }
+  if (primal) axpy_pass(c, c.Bt, c.ldb, n, v_x, ne + ni, v_se, nullptr, 1.0); // [A x; C x] (se, rup contiguous)
+}
+
+__device__ __noinline__ void global_primal_residual(Ctx& c, const Scal& sc, const pqp_settings& S, Glob& g)
+{
+  PQP_VECS(c);
+  const int n = c.n, ne = c.ne, ni = c.ni, nc = c.nc;
+  double mx[5] = { 0, 0, 0, 0, 0 }; // eq_rhs0, in_rhs0, eq_lhs, in_lhs, |x| stuff
+  double dummy[1] = { 0 };
+  const double* de = v_delta + n;
+  const double* di = v_delta + n + ne;
+  const double* db = v_delta + n + ne + ni;
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ne; i += NT) {
+    double v = v_se[i] / de[i];
+    mx[0] = nanmax(mx[0], fabs(v));
+    v -= v_b[i];
+    mx[2] = nanmax(mx[2], fabs(v));
+    v_se[i] = v; // unscaled Ax - b, rescaled below
+  }
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < nc; i += NT) {
+    double v;
+    if (i < ni) {
+      v = v_rup[i] / di[i];
+      mx[1] = nanmax(mx[1], fabs(v));
+    } else {
+      v = v_x[i - ni] * v_delta[i - ni]; // unscale_primal
+    }
+    v_rup[i] = v;
+    double sv = fmax(v - v_u[i], 0.0) + fmin(v - v_l[i], 0.0);
+    v_si[i] = sv;
+    mx[3] = nanmax(mx[3], fabs(sv));
+    if (i >= ni) {
+      // quirk kept: active_part_z.tail = x(scaled) - si ; rhs_0 also takes |x| (scaled), utils.hpp:225-231
+      mx[1] = nanmax(mx[1], fabs(v_x[i - ni] - sv));
+      mx[1] = nanmax(mx[1], fabs(v_x[i - ni]));
+    }
+  }
+  (void)db;
+  block_reduce<0, 4>(c, dummy, mx);
+  g.pri_eq_rhs0 = mx[0];
+  g.pri_in_rhs0 = mx[1];
+  g.pri_eq_lhs = mx[2];
+  g.pri_in_lhs = mx[3];
+  g.pri_lhs = fmax(mx[2], mx[3]);
+  if (S.primal_infeasibility_solving && sc.status == PQP_PRIMAL_INFEASIBLE) {
+    // (v_ex is free between Newton steps; t1..t3 may hold H x, A^T y, C^T z)
+    axpy_pass(c, c.Am, n, ne, v_se, n, v_ex, nullptr, 1.0);
+    axpy_pass(c, c.Cm, n, ni, v_si, n, v_ex, v_ex, 1.0);
+    double m = 0;
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) m = nanmax(m, fabs(v_ex[j]));
+    g.pri_lhs = block_max1(c, m);
+  }
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ne; i += NT) v_se[i] *= de[i];
+  __syncthreads();
+}
+
+// utils.hpp:439-587
+__device__ __noinline__ void global_dual_residual(Ctx& c, const Scal& sc, Glob& g)
+{
+  PQP_VECS(c);
+  const int n = c.n, ne = c.ne, ni = c.ni, nc = c.nc;
+  const double cs = c.c_scale;
+  // t1 = H x, t2 = A^T y, t3 = C^T z_C were produced by global_passes()
+  double sm[6] = { 0, 0, 0, 0, 0, 0 }; // g.x, xHx, b.y, zu, zl, (unused)
+  double mx[4] = { 0, 0, 0, 0 };       // rhs0, rhs1, rhs3, lhs
+  const double inf_b = 1.3407807929942596e+154; // sqrt(DBL_MAX), helpers/common.hpp:20-24
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
+    const double dxc = v_delta[j] * cs;
+    double hx = v_t1[j], aty = v_t2[j], ctz = v_t3[j];
+    double zb = c.box ? v_z[ni + j] * v_is[j] : 0.0;
+    double dr = v_gs[j] + hx + aty + ctz + zb;
+    v_dual[j] = dr;
+    const double hxu = hx / dxc;
+    mx[0] = nanmax(mx[0], fabs(hxu));
+    mx[1] = nanmax(mx[1], fabs(aty / dxc));
+    mx[2] = nanmax(mx[2], fabs(ctz / dxc));
+    if (c.box) mx[2] = nanmax(mx[2], fabs(zb / dxc));
+    mx[3] = nanmax(mx[3], fabs(dr / dxc));
+    const double xu = v_x[j] * v_delta[j];
+    sm[0] += (v_gs[j] / dxc) * xu; // model.g = gs / (delta c)
+    sm[1] += hxu * xu;
+  }
+  const double* de = v_delta + n;
+  const double* di = v_delta + n + ne;
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ne; i += NT) sm[2] += v_b[i] * (v_y[i] * de[i] / cs);
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < nc; i += NT) {
+    double zu_ = v_z[i] * di[i] / cs; // delta laid out [x | eq | in | box]: di[i] covers box too
+    if (c.act_up[i]) sm[3] += zu_ * fmin(v_u[i], inf_b);
+    if (c.act_low[i]) sm[4] += zu_ * fmax(v_l[i], -inf_b);
+  }
+  block_reduce<5, 4>(c, sm, mx);
+  g.dua_rhs0 = (c.hess == PQP_HESSIAN_ZERO) ? 0.0 : mx[0];
+  g.dua_rhs1 = mx[1];
+  g.dua_rhs3 = mx[2];
+  g.dua_lhs = mx[3];
+  double gap = sm[0];
+  double rhs_gap = fabs(gap);
+  if (c.hess != PQP_HESSIAN_ZERO) {
+    gap += sm[1];
+    rhs_gap = fmax(rhs_gap, fabs(sm[1]));
+  }
+  rhs_gap = fmax(rhs_gap, fabs(sm[2]));
+  gap += sm[2];
+  rhs_gap = fmax(rhs_gap, fabs(sm[3]));
+  gap += sm[3];
+  rhs_gap = fmax(rhs_gap, fabs(sm[4]));
+  gap += sm[4];
+  g.gap = gap;
+  g.rhs_gap = rhs_gap;
+  (void)sc;
+}
+
+// coefficients of phi'(alpha) = a alpha + b that do not depend on alpha
+// (linesearch.hpp:85-119, 133-134, 159-160 for GPDAL; :213-255, 288-304 for PDAL)
+struct LsBase
+{
+  double a0, b0;
+};
+
+__device__ __noinline__ LsBase ls_base(const Ctx& c, const Scal& sc, const pqp_settings& S)
+{
+  PQP_VECS(c);
+  const int n = c.n, ne = c.ne, nc = c.nc;
+  const bool gpdal = S.merit_function_type == PQP_MERIT_GPDAL;
+  double sm[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+  double dummy[1] = { 0 };
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
+    double dxj = v_dx[j];
+    sm[0] += dxj * v_hdx[j];
+    sm[1] += dxj * dxj;
+    sm[2] += v_x[j] * v_hdx[j];
+    sm[3] += (sc.rho * (v_x[j] - v_xp[j]) + v_gs[j]) * dxj;
+  }
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ne; i += NT) {
+    double ad = v_adx[i];
+    double e = ad - v_ds[i] * sc.mu_eq;
+    sm[4] += ad * ad;
+    sm[5] += e * e;
+    sm[6] += ad * (v_se[i] + v_y[i] * sc.mu_eq);
+    sm[7] += e * v_se[i];
+  }
+  if (gpdal) {
+    _Pragma("unroll 1") for (int i = threadIdx.x; i < nc; i += NT) {
+      sm[8] += v_dz[i] * v_dz[i];
+      sm[9] += v_dz[i] * v_z[i];
+    }
+  }
+  block_reduce<10, 0>(c, sm, dummy);
+  LsBase r;
+  const double nu = gpdal ? 1.0 : sc.nu;
+  r.a0 = sm[0] + sc.mu_eq_inv * sm[4] + sc.rho * sm[1] + sm[5] * sc.mu_eq_inv * nu;
+  r.b0 = sm[2] + sm[3] + sc.mu_eq_inv * sm[6] + nu * sc.mu_eq_inv * sm[7];
+  if (gpdal) {
+    r.a0 += sc.mu_in * (1.0 - S.alpha_gpdal) * sm[8];
+    r.b0 += sc.mu_in * (1.0 - S.alpha_gpdal) * sm[9];
+  }
+  return r;
+}
+
+// alpha-dependent part, evaluated by ONE thread over all constraints
+// (linesearch.hpp:121-152 / 257-304)
+__device__ __forceinline__ void ls_eval(const Ctx& c, const Scal& sc, const pqp_settings& S, const LsBase& base, double alpha, double& a, double& b)
+{
+  PQP_VECS(c);
+  const bool gpdal = S.merit_function_type == PQP_MERIT_GPDAL;
+  double sq = 0, dt = 0, sq2 = 0, dt2 = 0;
+  for (int i = 0; i < c.nc; ++i) {
+    const double cd = v_cdx[i], ru = v_rup[i], sl = v_si[i];
+    const bool up = (ru + cd * alpha) > 0.0;
+    const bool low = (sl + cd * alpha) < 0.0;
+    const double cact = (up || low) ? cd : 0.0;
+    const double apz = (up ? ru : 0.0) + (low ? sl : 0.0);
+    sq += cact * cact;
+    dt += apz * cact;
+    if (!gpdal) {
+      const double e = cact - v_dz[i] * sc.mu_in;
+      const double f = apz - v_z[i] * sc.mu_in;
+      sq2 += e * e;
+      dt2 += e * f;
+    }
+  }
+  if (gpdal) {
+    a = base.a0 + sc.mu_in_inv * sq / S.alpha_gpdal;
+    b = base.b0 + sc.mu_in_inv * dt / S.alpha_gpdal;
+  } else {
+    a = base.a0 + sc.mu_in_inv * sq + sc.nu * sc.mu_in_inv * sq2;
+    b = base.b0 + sc.mu_in_inv * dt + sc.nu * sc.mu_in_inv * dt2;
+  }
+}
+
+// Exact line search, linesearch.hpp:322-538. Breakpoints are evaluated in
+// parallel (one thread each); phi' is non-decreasing, so "first breakpoint
+// with phi' >= 0" / "last with phi' < 0" are a min / max reduction instead of
+// the reference's sort + sequential scan.
+__device__ __noinline__ double primal_dual_ls(Ctx& c, const Scal& sc, const pqp_settings& S)
+{
+  PQP_VECS(c);
+  const double eps = 2.220446049250313e-16;
+  const int nc = c.nc;
+  LsBase base = ls_base(c, sc, S);
+  if (threadIdx.x == 0) c.iscratch[2 * NW] = 0;
+  __syncthreads();
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < nc; i += NT) {
+    const double cd = v_cdx[i];
+    if (cd != 0.0) {
+      double a1 = -v_rup[i] / (cd + eps);
+      if (a1 > eps) v_alphas[atomicAdd(&c.iscratch[2 * NW], 1)] = a1;
+      double a2 = -v_si[i] / (cd + eps);
+      if (a2 > eps) v_alphas[atomicAdd(&c.iscratch[2 * NW], 1)] = a2;
+    }
+  }
+  __syncthreads();
+  const int n_alpha = c.iscratch[2 * NW];
+  // thread 0 of the last warp additionally evaluates alpha = 0
+  double best_pos_alpha = INFINITY, best_pos_grad = 0, best_neg_alpha = 0, best_neg_grad = 0;
+  _Pragma("unroll 1") for (int k = threadIdx.x; k < n_alpha + 1; k += NT) {
+    const double al = (k < n_alpha) ? v_alphas[k] : 0.0;
+    double a, b;
+    ls_eval(c, sc, S, base, al, a, b);
+    const double gr = a * al + b;
+    if (k == n_alpha) {
+      v_grads[0] = a;
+      v_grads[1] = b; // phi'(0) pieces
+    } else if (gr < 0.0) {
+      if (al > best_neg_alpha) {
+        best_neg_alpha = al;
+        best_neg_grad = gr;
+      }
+    } else if (al < best_pos_alpha) {
+      best_pos_alpha = al;
+      best_pos_grad = gr;
+    }
+  }
+  // reduce (alpha, grad) pairs: min over positives, max over negatives
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double pa = __shfl_xor_sync(FULL, best_pos_alpha, o), pg = __shfl_xor_sync(FULL, best_pos_grad, o);
+    if (pa < best_pos_alpha) {
+      best_pos_alpha = pa;
+      best_pos_grad = pg;
+    }
+    double na = __shfl_xor_sync(FULL, best_neg_alpha, o), ng = __shfl_xor_sync(FULL, best_neg_grad, o);
+    if (na > best_neg_alpha) {
+      best_neg_alpha = na;
+      best_neg_grad = ng;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    v_red[warp * 4 + 0] = best_pos_alpha;
+    v_red[warp * 4 + 1] = best_pos_grad;
+    v_red[warp * 4 + 2] = best_neg_alpha;
+    v_red[warp * 4 + 3] = best_neg_grad;
+  }
+  __syncthreads();
+  double alpha_first_pos = INFINITY, first_pos_grad = 0, alpha_last_neg = 0, last_neg_grad = 0;
+  for (int w = 0; w < NW; ++w) {
+    if (v_red[w * 4 + 0] < alpha_first_pos) {
+      alpha_first_pos = v_red[w * 4 + 0];
+      first_pos_grad = v_red[w * 4 + 1];
+    }
+    if (v_red[w * 4 + 2] > alpha_last_neg) {
+      alpha_last_neg = v_red[w * 4 + 2];
+      last_neg_grad = v_red[w * 4 + 3];
+    }
+  }
+  const double a0 = v_grads[0], b0 = v_grads[1];
+  __syncthreads();
+  if (n_alpha == 0) return -b0 / a0;
+  // the reference stops its scan at the first non-negative gradient, so
+  // negatives beyond it are never seen (linesearch.hpp:460-467)
+  if (alpha_last_neg > alpha_first_pos) {
+    // not monotone to rounding: fall back to the breakpoint just below
+    alpha_last_neg = 0;
+  }
+  if (alpha_last_neg == 0.0) last_neg_grad = b0; // phi'(0) = a*0 + b
+  if (alpha_first_pos == INFINITY) {
+    double a, b;
+    ls_eval(c, sc, S, base, 2 * alpha_last_neg + 1, a, b);
+    return -b / a;
+  }
+  return fabs(alpha_last_neg - last_neg_grad * (alpha_first_pos - alpha_last_neg) / (first_pos_grad - last_neg_grad));
+}
+
+__device__ __forceinline__ unsigned long long gtimer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ void dbg_write(const PqpSolveArgs& A, int q, int& pos, double a, double b, double c0, double d, double e, double f)
+{
+  if (A.dbg && q == A.dbg_qp && threadIdx.x == 0 && pos + 6 <= A.dbg_cap) {
+    A.dbg[pos + 0] = a;
+    A.dbg[pos + 1] = b;
+    A.dbg[pos + 2] = c0;
+    A.dbg[pos + 3] = d;
+    A.dbg[pos + 4] = e;
+    A.dbg[pos + 5] = f;
+    pos += 6;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// one QP, start to finish: dense/solver.hpp:1088-1843
+// ---------------------------------------------------------------------------
+__device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
+{
+  PQP_VECS(c);
+  const PqpQpParams& prm = A.p.params[q];
+  const pqp_settings& S = prm.s;
+  const int n = c.n, ne = c.ne, ni = c.ni, nc = c.nc;
+  const int tid = threadIdx.x;
+  int dbg_pos = 0;
+  const long long t_qp = PROF_T0();
+  long long tph = t_qp;
+
+  // ---- stage the per-QP data in shared memory --------------------------------
+  {
+    const PqpBatchPtrs& P = A.p;
+    const double* Asg = P.As + (size_t)q * ne * n;
+    if (tid == 0) {
+      c.Hs = P.Hs + (size_t)q * n * n;
+      c.Cs = P.Cs + (size_t)q * ni * n;
+      c.Hm = P.H + (size_t)q * n * n;
+      c.Am = P.A + (size_t)q * ne * n;
+      c.Cm = P.C + (size_t)q * ni * n;
+      c.As = const_cast<double*>(Asg);
+    }
+    __syncthreads();
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_gs[j] = P.gs[(size_t)q * n + j];
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) {
+      v_bs[j] = P.bs[(size_t)q * ne + j];
+      v_b[j] = P.b[(size_t)q * ne + j];
+    }
+    _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) {
+      v_us[j] = P.us[(size_t)q * nc + j];
+      v_ls[j] = P.ls[(size_t)q * nc + j];
+      if (j < ni) {
+        v_u[j] = P.u[(size_t)q * ni + j];
+        v_l[j] = P.l[(size_t)q * ni + j];
+      } else {
+        v_u[j] = P.u_box[(size_t)q * n + j - ni];
+        v_l[j] = P.l_box[(size_t)q * n + j - ni];
+      }
+      c.cons_slot[j] = -1;
+      c.act_up[j] = 0;
+      c.act_low[j] = 0;
+    }
+    _Pragma("unroll 1") for (int j = tid; j < n + ne + nc; j += NT) v_delta[j] = P.delta[(size_t)q * (n + ne + nc) + j];
+    if (tid == 0) {
+      c.c_scale = P.c[q];
+      c.ns = 0;
+      c.overflow = 0;
+    }
+    __syncthreads();
+  }
+  const double cs = c.c_scale;
+  const double* dlx = v_delta;
+  const double* dle = v_delta + n;
+  const double* dli = v_delta + n + ne; // covers box entries too ([in | box] contiguous)
+
+  Scal sc;
+  sc.rho = prm.rho;
+  sc.mu_eq = prm.mu_eq;
+  sc.mu_in = prm.mu_in;
+  sc.mu_eq_inv = 1.0 / sc.mu_eq;
+  sc.mu_in_inv = 1.0 / sc.mu_in;
+  sc.nu = 1.0;
+  sc.iter = 0;
+  sc.iter_ext = 0;
+  sc.mu_updates = 0;
+  sc.status = PQP_MAX_ITER_REACHED;
+  sc.iterative_residual = 0;
+  sc.factor_fresh = true;
+
+  // ---- initial iterate (solver.hpp:1125-1377) --------------------------------
+  if (prm.start_mode == PQP_START_WARM || prm.start_mode == PQP_START_WARM_KEEP) {
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_x[j] = A.p.x[(size_t)q * n + j] / dlx[j];
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_y[j] = A.p.y[(size_t)q * ne + j] / dle[j] * cs;
+    _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) v_z[j] = A.p.z[(size_t)q * nc + j] / dli[j] * cs;
+  } else {
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_x[j] = 0;
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_y[j] = 0;
+    _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) v_z[j] = 0;
+  }
+  _Pragma("unroll 1") for (int j = tid; j < n; j += NT) {
+    v_rx[j] = 0;
+    v_dx[j] = 0;
+  }
+  _Pragma("unroll 1") for (int j = tid; j < c.cap; j += NT) {
+    v_rs[j] = 0;
+    v_ds[j] = 0;
+  }
+  _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_se[j] = 0;
+  _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) {
+    v_si[j] = 0;
+    v_dz[j] = 0;
+  }
+  __syncthreads();
+
+  PROF_ADD(PH_STAGE, tph);
+  // ---- first factorisation (helpers.hpp:241-285) -----------------------------
+  tph = PROF_T0();
+  build_Bt(c);
+  build_Pi(c, sc.rho);
+  PROF_ADD(PH_M1, tph);
+  tph = PROF_T0();
+  build_dual_block(c, ne, sc.mu_eq, sc.mu_in);
+  PROF_ADD(PH_EQ, tph);
+
+  if (prm.start_mode == PQP_START_EQ_GUESS) {
+    // helpers.hpp:201-228
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_rx[j] = -v_gs[j];
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_rs[j] = v_bs[j];
+    __syncthreads();
+    iterative_solve(c, sc, S, 1.0);
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) {
+      v_x[j] = v_dx[j];
+      v_dx[j] = 0;
+    }
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) {
+      v_y[j] = v_ds[j];
+      v_ds[j] = 0;
+    }
+    __syncthreads();
+  } else if (prm.start_mode == PQP_START_WARM || prm.start_mode == PQP_START_WARM_KEEP) {
+    // active set := { i : z_i != 0 } (solver.hpp:1300-1309)
+    _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
+      c.act_up[i] = (v_z[i] != 0.0);
+      c.act_low[i] = 0;
+    }
+    __syncthreads();
+    active_set_change(c, sc);
+    _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) c.act_up[i] = 0;
+    __syncthreads();
+  }
+  const bool overflow_at_start = c.overflow != 0;
+
+  double bcl_eta_ext_init = pow(0.1, S.alpha_bcl);
+  double bcl_eta_ext = bcl_eta_ext_init;
+  double bcl_eta_in = 1.0;
+  const double eps_in_min = fmin(S.eps_abs, 1e-9);
+  double scaled_eps = S.eps_abs;
+  Glob g;
+  g.pri_lhs = g.pri_eq_rhs0 = g.pri_in_rhs0 = g.pri_eq_lhs = g.pri_in_lhs = 0;
+  g.dua_lhs = g.dua_rhs0 = g.dua_rhs1 = g.dua_rhs3 = g.gap = g.rhs_gap = 0;
+  const double dual_rhs2 = [&]() {
+    double m = 0;
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) m = nanmax(m, fabs(v_gs[j] / (dlx[j] * cs)));
+    return block_max1(c, m);
+  }(); // |model.g|_inf (helpers.hpp:651)
+  double info_pri = 0, info_dua = 0, info_gap = 0;
+  bool infeasible_exit = false;
+  bool expired = false; // watchdog (debug aid, off by default)
+  const unsigned long long t_start = A.watchdog_ns ? gtimer_ns() : 0ull;
+
+  bool residuals_fresh = false;
+  for (long long iter = 0; iter < S.max_iter && !overflow_at_start; ++iter) {
+    // The reference recomputes both global residuals here; from the second
+    // outer iteration on they were already evaluated for exactly this
+    // (x, y, z) at the end of the previous iteration, so the values are reused
+    // (identical numbers, one streaming pass over H, A, C saved).
+    tph = PROF_T0();
+    if (!residuals_fresh) {
+      global_passes(c, true, true);
+      global_primal_residual(c, sc, S, g);
+      global_dual_residual(c, sc, g);
+    }
+    PROF_ADD(PH_GLOBAL, tph);
+    double primal_feasibility_lhs = g.pri_lhs;
+    double dual_feasibility_lhs = g.dua_lhs;
+    info_pri = g.pri_lhs;
+    info_dua = g.dua_lhs;
+    info_gap = g.gap;
+    dbg_write(A, q, dbg_pos, (double)iter, g.pri_lhs, g.dua_lhs, sc.mu_in, (double)(c.ns - ne), (double)sc.iter);
+
+    double new_mu_in = sc.mu_in, new_mu_eq = sc.mu_eq, new_mu_in_inv = sc.mu_in_inv, new_mu_eq_inv = sc.mu_eq_inv;
+    double rhs_pri = scaled_eps;
+    if (S.eps_rel != 0) rhs_pri += S.eps_rel * fmax(g.pri_eq_rhs0, g.pri_in_rhs0);
+    bool is_primal_feasible = primal_feasibility_lhs <= rhs_pri;
+    double rhs_dua = S.eps_abs;
+    if (S.eps_rel != 0) rhs_dua += S.eps_rel * fmax(fmax(g.dua_rhs3, g.dua_rhs0), fmax(g.dua_rhs1, dual_rhs2));
+    bool is_dual_feasible = dual_feasibility_lhs <= rhs_dua;
+    if (is_primal_feasible && is_dual_feasible) {
+      if (S.check_duality_gap) {
+        if (fabs(g.gap) <= S.eps_duality_gap_abs + S.eps_duality_gap_rel * g.rhs_gap) {
+          sc.status = (S.primal_infeasibility_solving && sc.status == PQP_PRIMAL_INFEASIBLE) ? PQP_SOLVED_CLOSEST_PRIMAL_FEASIBLE : PQP_SOLVED;
+          break;
+        }
+      } else {
+        sc.status = PQP_SOLVED;
+        break;
+      }
+    }
+    sc.iter_ext += 1;
+    // x_prev..; shifted residuals (solver.hpp:1517-1559)
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_xp[j] = v_x[j];
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_yp[j] = v_y[j];
+    const double ag = (S.merit_function_type == PQP_MERIT_GPDAL) ? S.alpha_gpdal : 1.0;
+    _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
+      const double zi = v_z[i];
+      v_zp[i] = zi;
+      double v = v_rup[i] * dli[i]; // scaled C x (box: scaled x-bound residual)
+      v += zi * sc.mu_in;
+      if (S.merit_function_type == PQP_MERIT_GPDAL) v += (S.alpha_gpdal - 1.0) * sc.mu_in * zi;
+      v_rup[i] = v - v_us[i];
+      v_si[i] = v - v_ls[i];
+    }
+    __syncthreads();
+
+    // ---- inner loop: primal_dual_newton_semi_smooth (solver.hpp:884-1077) ----
+    {
+      const double eps_int = bcl_eta_in;
+      for (long long it_in = 0; it_in <= S.max_iter_in; ++it_in) {
+        if (it_in == S.max_iter_in) {
+          sc.iter += S.max_iter_in + 1;
+          break;
+        }
+        if (A.watchdog_ns) {
+          if (tid == 0) c.iscratch[2 * NW + 1] = (gtimer_ns() - t_start > A.watchdog_ns) ? 1 : 0;
+          __syncthreads();
+          expired = c.iscratch[2 * NW + 1] != 0;
+          __syncthreads();
+          if (expired) break;
+        }
+        // -- Newton step (solver.hpp:756-869)
+        _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
+          c.act_up[i] = v_rup[i] >= 0.0;
+          c.act_low[i] = v_si[i] <= 0.0;
+        }
+        __syncthreads();
+        active_set_change(c, sc);
+        if (c.overflow) { // S^-1 capacity exceeded: the QP is re-solved by the generic kernel
+          expired = true;
+          break;
+        }
+        // q = sum over inactive constraints with z_i != 0 of z_i c_i
+        int nq = block_compact(c, nc, c.list2, [&](int i) { return c.cons_slot[i] < 0 && v_z[i] != 0.0; });
+        if (nq > 0) {
+          axpy_pass2(c, c.Cs, 0, c.Cs, n, c.list2, 1, nq, v_z, n, v_q, nullptr, 1.0);
+        } else {
+          _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_q[j] = 0;
+        }
+        _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_rx[j] = -v_dual[j] + v_q[j];
+        _Pragma("unroll 1") for (int s = tid; s < c.ns; s += NT) {
+          if (s < ne) {
+            v_rs[s] = -v_se[s];
+          } else {
+            const int i = c.slot_cons[s];
+            if (c.act_up[i])
+              v_rs[s] = -v_rup[i] + v_z[i] * sc.mu_in * ag;
+            else
+              v_rs[s] = -v_si[i] + v_z[i] * sc.mu_in * ag;
+          }
+        }
+        __syncthreads();
+        iterative_solve(c, sc, S, eps_int);
+        // un-permute dz; Cdx, CTdz (solver.hpp:860-967)
+        _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
+          const int s = c.cons_slot[i];
+          const double dzi = (s >= 0) ? v_ds[s] : -v_z[i];
+          v_dz[i] = dzi;
+          if (S.merit_function_type == PQP_MERIT_GPDAL) v_cdx[i] += (S.alpha_gpdal - 1.0) * sc.mu_in * dzi;
+        }
+        _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_atdy[j] -= v_q[j]; // atdy now holds A^T dy + C^T dz
+        __syncthreads();
+        double alpha = 1.0;
+        tph = PROF_T0();
+        if (ni > 0 || c.box) alpha = primal_dual_ls(c, sc, S);
+        PROF_ADD(PH_LS, tph);
+        // |alpha dw|_inf
+        {
+          double m = 0;
+          _Pragma("unroll 1") for (int j = tid; j < n; j += NT) m = nanmax(m, fabs(v_dx[j]));
+          _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) m = nanmax(m, fabs(v_ds[j]));
+          _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) m = nanmax(m, fabs(v_dz[i]));
+          m = block_max1(c, m);
+          if (m * fabs(alpha) < 1e-11 && it_in > 0) {
+            sc.iter += it_in + 1;
+            break;
+          }
+        }
+        // iterate update + inner residual + infeasibility tests, fused
+        double sm[6] = { 0, 0, 0, 0, 0, 0 }; // lb1 (primal inf), gdx
+        double mx[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        // mx: 0 err_in | 1 |dy|u 2 |dz|u 3 |ATdy+CTdz|u 4 |dy|s,|dz|s any nonzero | 5 |dx|u 6 |Adx|u 7 |Hdx|u 8 first_cond violation 9 spare
+        _Pragma("unroll 1") for (int j = tid; j < n; j += NT) {
+          const double dxj = v_dx[j];
+          v_x[j] += alpha * dxj;
+          double dr = v_dual[j] + alpha * (sc.rho * dxj + v_hdx[j] + v_atdy[j]);
+          v_dual[j] = dr;
+          mx[0] = nanmax(mx[0], fabs(dr));
+          const double dxc = dlx[j] * cs;
+          mx[3] = nanmax(mx[3], fabs(v_atdy[j] / dxc));
+          const double dxu = dxj * dlx[j];
+          mx[5] = nanmax(mx[5], fabs(dxu));
+          mx[7] = nanmax(mx[7], fabs(v_hdx[j] / dxc));
+          sm[1] += dxj * v_gs[j];
+        }
+        _Pragma("unroll 1") for (int i = tid; i < ne; i += NT) {
+          const double dyi = v_ds[i];
+          double sev = v_se[i] + alpha * (v_adx[i] - sc.mu_eq * dyi);
+          v_se[i] = sev;
+          v_y[i] += alpha * dyi;
+          mx[0] = nanmax(mx[0], fabs(sev));
+          mx[4] = nanmax(mx[4], fabs(dyi));
+          sm[0] += dyi * v_bs[i];
+          mx[1] = nanmax(mx[1], fabs(dyi * dle[i] / cs));
+          mx[6] = nanmax(mx[6], fabs(v_adx[i] / dle[i]));
+        }
+        _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
+          const double dzi = v_dz[i], cd = v_cdx[i];
+          const double ru = v_rup[i] + alpha * cd;
+          const double sl = v_si[i] + alpha * cd;
+          const double zi = v_z[i] + alpha * dzi;
+          v_rup[i] = ru;
+          v_si[i] = sl;
+          v_z[i] = zi;
+          const double apz = fmax(ru, 0.0) + fmin(sl, 0.0) - ag * zi * sc.mu_in;
+          mx[0] = nanmax(mx[0], fabs(apz));
+          mx[4] = nanmax(mx[4], fabs(dzi));
+          sm[0] += fmax(dzi, 0.0) * v_us[i] - fmin(dzi, 0.0) * v_ls[i];
+          mx[2] = nanmax(mx[2], fabs(dzi * dli[i] / cs));
+        }
+        block_reduce<2, 8>(c, sm, mx);
+        const double err_in = mx[0];
+        if (it_in % S.frequence_infeasibility_check == 0 || S.primal_infeasibility_solving) {
+          // utils.hpp:271-324
+          bool is_primal_infeasible = false;
+          if (mx[4] != 0.0) {
+            const double upper = S.eps_primal_inf * fmax(mx[1], mx[2]);
+            is_primal_infeasible = mx[3] <= upper && sm[0] <= -upper;
+          }
+          // utils.hpp:345-419
+          bool is_dual_infeasible = false;
+          {
+            double bound = mx[5] * S.eps_dual_inf;
+            double viol = 0;
+            _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
+              const double v = v_cdx[i] / dli[i]; // unscaled (box entries use delta_box)
+              bool ok = true;
+              if (v_us[i] <= 1e20 && v_ls[i] >= -1e20)
+                ok = v <= bound && v >= -bound;
+              else if (v_us[i] > 1e20)
+                ok = v >= -bound;
+              else if (v_ls[i] < -1e20)
+                ok = v <= bound;
+              if (!ok) viol = 1.0;
+            }
+            viol = block_max1(c, viol);
+            bool first_cond = mx[6] <= bound && viol == 0.0;
+            bound *= cs;
+            bool second = mx[7] <= bound && sm[1] <= -bound;
+            is_dual_infeasible = first_cond && second && mx[5] != 0.0;
+          }
+          if (is_primal_infeasible) {
+            sc.status = PQP_PRIMAL_INFEASIBLE;
+            if (!S.primal_infeasibility_solving) {
+              sc.iter += it_in + 1;
+              break;
+            }
+          } else if (is_dual_infeasible) {
+            sc.status = PQP_DUAL_INFEASIBLE;
+            sc.iter += it_in + 1;
+            break;
+          }
+        }
+        if (err_in <= eps_int) {
+          sc.iter += it_in + 1;
+          break;
+        }
+      }
+    }
+    if (expired) break;
+    if ((sc.status == PQP_PRIMAL_INFEASIBLE && !S.primal_infeasibility_solving) || sc.status == PQP_DUAL_INFEASIBLE) {
+      // certificate of infeasibility: the (already unscaled, quirk 4) step
+      _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_x[j] = v_dx[j] * dlx[j];
+      _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_y[j] = v_ds[j] * dle[j] / cs;
+      _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) v_z[i] = v_dz[i] * dli[i] / cs;
+      __syncthreads();
+      infeasible_exit = true;
+      break;
+    }
+    if (scaled_eps == S.eps_abs && S.primal_infeasibility_solving && sc.status == PQP_PRIMAL_INFEASIBLE) {
+      // solver.hpp:1581-1595
+      _Pragma("unroll 1") for (int j = tid; j < ne + ni; j += NT) c.kt[j] = 1.0;
+      __syncthreads();
+      axpy_pass(c, c.Am, n, ne, c.kt, n, v_t1, nullptr, 1.0);
+      axpy_pass(c, c.Cm, n, ni, c.kt, n, v_t1, v_t1, 1.0);
+      double m = 0;
+      _Pragma("unroll 1") for (int j = tid; j < n; j += NT) m = nanmax(m, fabs(v_t1[j] + (c.box ? v_is[j] : 0.0)));
+      scaled_eps = block_max1(c, m) * S.eps_abs;
+    }
+    tph = PROF_T0();
+    global_passes(c, true, false);
+    global_primal_residual(c, sc, S, g);
+    PROF_ADD(PH_GLOBAL, tph);
+    bool dual_done = false; // dual residual already evaluated for the current (x, y, z)
+    double primal_feasibility_lhs_new = g.pri_lhs;
+    is_primal_feasible = primal_feasibility_lhs_new <= (scaled_eps + S.eps_rel * fmax(g.pri_eq_rhs0, g.pri_in_rhs0));
+    info_pri = primal_feasibility_lhs_new;
+    if (is_primal_feasible) {
+      tph = PROF_T0();
+      global_passes(c, false, true);
+      global_dual_residual(c, sc, g);
+      PROF_ADD(PH_GLOBAL, tph);
+      dual_done = true;
+      info_dua = g.dua_lhs;
+      info_gap = g.gap;
+      is_dual_feasible = g.dua_lhs <= (S.eps_abs + S.eps_rel * fmax(fmax(g.dua_rhs3, g.dua_rhs0), fmax(g.dua_rhs1, dual_rhs2)));
+      if (is_dual_feasible) {
+        bool gap_ok = !S.check_duality_gap || fabs(g.gap) <= S.eps_duality_gap_abs + S.eps_duality_gap_rel * g.rhs_gap;
+        if (gap_ok) sc.status = (S.primal_infeasibility_solving && sc.status == PQP_PRIMAL_INFEASIBLE) ? PQP_SOLVED_CLOSEST_PRIMAL_FEASIBLE : PQP_SOLVED;
+      }
+    }
+    if (S.bcl_update) {
+      // solver.hpp:566-614
+      if (primal_feasibility_lhs_new <= bcl_eta_ext || sc.iter > S.safe_guard) {
+        bcl_eta_ext *= pow(sc.mu_in, S.beta_bcl);
+        bcl_eta_in = fmax(bcl_eta_in * sc.mu_in, eps_in_min);
+      } else {
+        _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_y[j] = v_yp[j];
+        _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) v_z[i] = v_zp[i];
+        __syncthreads();
+        dual_done = false;
+        new_mu_in = fmax(sc.mu_in * S.mu_update_factor, S.mu_min_in);
+        new_mu_eq = fmax(sc.mu_eq * S.mu_update_factor, S.mu_min_eq);
+        new_mu_in_inv = fmin(sc.mu_in_inv * S.mu_update_inv_factor, S.mu_max_in_inv);
+        new_mu_eq_inv = fmin(sc.mu_eq_inv * S.mu_update_inv_factor, S.mu_max_eq_inv);
+        bcl_eta_ext = bcl_eta_ext_init * pow(new_mu_in, S.alpha_bcl);
+        bcl_eta_in = fmax(new_mu_in, eps_in_min);
+      }
+    } else {
+      // solver.hpp:639-677
+      bcl_eta_in = fmax(bcl_eta_in * 0.1, eps_in_min);
+      if (!(primal_feasibility_lhs_new <= 0.95 * primal_feasibility_lhs)) {
+        new_mu_in = fmax(sc.mu_in * S.mu_update_factor, S.mu_min_in);
+        new_mu_eq = fmax(sc.mu_eq * S.mu_update_factor, S.mu_min_eq);
+        new_mu_in_inv = fmin(sc.mu_in_inv * S.mu_update_inv_factor, S.mu_max_in_inv);
+        new_mu_eq_inv = fmin(sc.mu_eq_inv * S.mu_update_inv_factor, S.mu_max_eq_inv);
+      }
+    }
+    tph = PROF_T0();
+    if (!dual_done) {
+      global_passes(c, false, true);
+      global_dual_residual(c, sc, g);
+    }
+    PROF_ADD(PH_GLOBAL, tph);
+    residuals_fresh = true;
+    const double dual_feasibility_lhs_new = g.dua_lhs;
+    info_dua = g.dua_lhs;
+    info_gap = g.gap;
+    if (primal_feasibility_lhs_new >= primal_feasibility_lhs && dual_feasibility_lhs_new >= dual_feasibility_lhs && sc.mu_in <= 1e-5) {
+      new_mu_in = S.cold_reset_mu_in;
+      new_mu_eq = S.cold_reset_mu_eq;
+      new_mu_in_inv = S.cold_reset_mu_in_inv;
+      new_mu_eq_inv = S.cold_reset_mu_eq_inv;
+    }
+    if (sc.mu_in != new_mu_in || sc.mu_eq != new_mu_eq) {
+      ++sc.mu_updates;
+      if (c.ns > 0) {
+        tph = PROF_T0();
+        rebuild_Si_from_G(c, new_mu_eq, new_mu_in);
+        PROF_ADD(PH_MU, tph);
+        sc.factor_fresh = false;
+      }
+    }
+    sc.mu_eq = new_mu_eq;
+    sc.mu_in = new_mu_in;
+    sc.mu_eq_inv = new_mu_eq_inv;
+    sc.mu_in_inv = new_mu_in_inv;
+  }
+
+  if (c.overflow) {
+    // leave x, y, z untouched (warm starts must see the caller's values again)
+    if (tid == 0) A.p.info[(size_t)q * PQP_INFO_DOUBLES + 10] = 99.0; // internal: retry with the generic kernel
+    __syncthreads();
+    return;
+  }
+  // ---- unscale and write back (solver.hpp:1749-1836) -------------------------
+  double* xo = A.p.x + (size_t)q * n;
+  double* yo = A.p.y + (size_t)q * ne;
+  double* zo = A.p.z + (size_t)q * nc;
+  double* seo = A.p.se + (size_t)q * ne;
+  double* sio = A.p.si + (size_t)q * nc;
+  const bool unscale_s = S.primal_infeasibility_solving && sc.status == PQP_PRIMAL_INFEASIBLE;
+  _Pragma("unroll 1") for (int j = tid; j < n; j += NT) {
+    const double xu = v_x[j] * dlx[j];
+    v_t1[j] = xu;
+    xo[j] = xu;
+  }
+  _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) {
+    yo[j] = v_y[j] * dle[j] / cs;
+    seo[j] = unscale_s ? v_se[j] / dle[j] : v_se[j];
+  }
+  _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
+    zo[i] = v_z[i] * dli[i] / cs;
+    sio[i] = unscale_s ? v_si[i] / dli[i] : v_si[i];
+  }
+  __syncthreads();
+  (void)infeasible_exit;
+  // objective 0.5 x^T H x + g^T x from the model (solver.hpp:1769-1781)
+  double obj;
+  {
+    axpy_pass(c, c.Hm, n, n, v_t1, n, v_t2, nullptr, 1.0);
+    double part = 0;
+    const double* gm = A.p.g + (size_t)q * n;
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) part += v_t1[j] * (0.5 * v_t2[j] + gm[j]);
+    obj = block_sum1(c, part);
+  }
+  if (tid == 0) {
+    double* I = A.p.info + (size_t)q * PQP_INFO_DOUBLES;
+    I[0] = sc.mu_eq;
+    I[1] = sc.mu_eq_inv;
+    I[2] = sc.mu_in;
+    I[3] = sc.mu_in_inv;
+    I[4] = sc.rho;
+    I[5] = sc.nu;
+    I[6] = (double)sc.iter;
+    I[7] = (double)sc.iter_ext;
+    I[8] = (double)sc.mu_updates;
+    I[9] = 0.0;
+    I[10] = (double)sc.status;
+    I[11] = 0;
+    I[12] = 0;
+    I[13] = 0;
+    I[14] = obj;
+    I[15] = info_pri;
+    I[16] = info_dua;
+    I[17] = info_gap;
+    I[18] = sc.iterative_residual;
+    I[19] = S.default_H_eigenvalue_estimate;
+  }
+  PROF_ADD(PH_TOTAL, t_qp);
+  __syncthreads();
+}
+
+extern __shared__ __align__(16) double smem_dyn[];
+
+__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArgs A)
+{
+  __shared__ Ctx c;
+  __shared__ int cur_q;
+  __shared__ long long prof_sh[PH_COUNT];
+  const PqpLayout& L = A.lay;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < PH_COUNT; ++k) prof_sh[k] = 0;
+    c.prof = A.prof ? prof_sh : nullptr;
+    c.vec_smem = 1;
+    c.pi_smem = 0;
+    c.si_cap = L.si_cap;
+    c.uv_ld = ((A.d.n > L.si_cap ? A.d.n : L.si_cap) + 2) & ~1;
+    c.ldb = (A.d.ne + A.d.ni + 1) & ~1;
+    c.ldn = (A.d.n + 1) & ~1;
+    c.overflow = 0;
+    double* ws = A.ws + (size_t)blockIdx.x * (size_t)L.ws_doubles;
+    auto place = [&](int id) -> double* { return (L.in_smem[id] ? smem_dyn : ws) + L.off[id]; };
+    c.n = A.d.n;
+    c.ne = A.d.ne;
+    c.ni = A.d.ni;
+    c.nc = A.d.nc;
+    c.box = A.d.box;
+    c.hess = A.d.hess;
+    c.cap = L.si_cap; // slot-indexed vectors are sized for the shared-memory S^-1
+    c.ns = 0;
+    c.Pi = place(PA_M1);
+    c.As = nullptr;
+    c.Bt = place(PA_AS); // the A_s slot of the workspace holds Bt in this layout
+    c.Si = place(PA_MS);
+    c.G = place(PA_G);
+    c.Y = place(PA_Y);
+    double* v = place(PA_VEC);
+    c.x = v + L.voff[V_X];
+    c.y = v + L.voff[V_Y];
+    c.z = v + L.voff[V_Z];
+    c.xp = v + L.voff[V_XP];
+    c.yp = v + L.voff[V_YP];
+    c.zp = v + L.voff[V_ZP];
+    c.dx = v + L.voff[V_DX];
+    c.ds = v + L.voff[V_DS];
+    c.dz = v + L.voff[V_DZ];
+    c.rx = v + L.voff[V_RX];
+    c.rs = v + L.voff[V_RS];
+    c.ex = v + L.voff[V_EX];
+    c.es = v + L.voff[V_ES];
+    c.dual = v + L.voff[V_DUAL];
+    c.se = v + L.voff[V_SE];
+    c.rup = v + L.voff[V_RUP];
+    c.si = v + L.voff[V_SI];
+    c.hdx = v + L.voff[V_HDX];
+    c.adx = v + L.voff[V_ADX];
+    c.atdy = v + L.voff[V_ATDY];
+    c.cdx = v + L.voff[V_CDX];
+    c.ctdz = v + L.voff[V_CTDZ];
+    c.q = v + L.voff[V_Q];
+    c.gs = v + L.voff[V_GS];
+    c.bs = v + L.voff[V_BS];
+    c.us = v + L.voff[V_US];
+    c.ls = v + L.voff[V_LS];
+    c.is = v + L.voff[V_IS];
+    c.delta = v + L.voff[V_DELTA];
+    c.b = v + L.voff[V_B];
+    c.u = v + L.voff[V_U];
+    c.l = v + L.voff[V_L];
+    c.d1inv = v + L.voff[V_D1INV];
+    c.dsv = v + L.voff[V_DSV];
+    c.dsinv = v + L.voff[V_DSINV];
+    c.t1 = v + L.voff[V_T1];
+    c.t2 = v + L.voff[V_T2];
+    c.t3 = v + L.voff[V_T3];
+    c.s1 = v + L.voff[V_S1];
+    c.s2 = v + L.voff[V_S2];
+    c.s3 = v + L.voff[V_S3];
+    c.s4 = v + L.voff[V_S4];
+    c.alphas = v + L.voff[V_ALPHAS];
+    c.grads = v + L.voff[V_GRADS];
+    c.scratch = v + L.voff[V_SCRATCH];
+    c.red = v + L.voff[V_RED];
+    c.kt = v + L.voff[V_KT];
+    int* ib = reinterpret_cast<int*>(smem_dyn + L.smem_doubles);
+    c.cons_slot = ib;
+    c.slot_cons = c.cons_slot + A.d.nc;
+    c.list1 = c.slot_cons + A.d.cap;
+    c.list2 = c.list1 + (A.d.nc > A.d.cap ? A.d.nc : A.d.cap);
+    c.iscratch = c.list2 + A.d.nc;
+    c.act_up = reinterpret_cast<unsigned char*>(c.iscratch + 2 * NW + 8);
+    c.act_low = c.act_up + A.d.nc;
+  }
+  __syncthreads();
+  while (true) {
+    if (threadIdx.x == 0) cur_q = atomicAdd(A.counter, 1);
+    __syncthreads();
+    const int q = cur_q;
+    __syncthreads();
+    if (q >= A.batch) break;
+    if (!A.p.params[q].active) continue;
+    solve_one(c, A, q);
+  }
+  if (A.prof && threadIdx.x == 0) {
+    for (int k = 0; k < PH_COUNT; ++k) atomicAdd(reinterpret_cast<unsigned long long*>(A.prof) + k, (unsigned long long)prof_sh[k]);
+  }
+}
+

@@ -38,6 +38,9 @@
 namespace fastk {
 #include "pqp_solver_body.inl"
 }
+namespace tilek {
+#include "pqp_fast_body.inl"
+}
 #undef PQP_SM
 #define PQP_SM(p) ((void)0)
 namespace genk {
@@ -353,7 +356,7 @@ pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream)
   // fast kernel: vectors and S^-1 in shared memory; P^-1 either there too or swept inside the S^-1 region
   const int64_t symn = (int64_t)a->d.n * (a->d.n + 1) / 2, symc = (int64_t)a->lay.si_cap * (a->lay.si_cap + 1) / 2;
   const bool fast = a->lay.in_smem[PA_VEC] && a->lay.in_smem[PA_MS] && (a->lay.in_smem[PA_M1] || a->d.hess != PQP_HESSIAN_DENSE || symn <= symc);
-  auto kern = fast ? fastk::pqp_solve_kernel : genk::pqp_solve_kernel;
+  auto kern = (a->lay.kind == 1) ? tilek::pqp_solve_kernel : (fast ? fastk::pqp_solve_kernel : genk::pqp_solve_kernel);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid, NT, smem, (cudaStream_t)stream>>>(*a);
