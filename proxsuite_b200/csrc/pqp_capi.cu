@@ -255,11 +255,11 @@ fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_ca
   L.kind = 1;
   const int ldn = (n + 1) & ~1, ldb = (ne + d.ni + 1) & ~1;
   int64_t sz[PA_COUNT];
-  sz[PA_M1] = rnd((int64_t)n * ldn + 2);
-  sz[PA_AS] = rnd((int64_t)n * ldb + 2); // Bt
+  sz[PA_M1] = rnd((int64_t)n * ldn + 4);
+  sz[PA_AS] = rnd((int64_t)n * ldb + 4);              // Bt
   sz[PA_MS] = rnd(tile_doubles(si_cap));
-  sz[PA_G] = rnd((int64_t)cap * (cap + 1) / 2 + 2);
-  sz[PA_Y] = 2;
+  sz[PA_G] = rnd((int64_t)(ne + d.ni) * ldb + 4);     // G, full square
+  sz[PA_Y] = rnd((int64_t)n * ldb + 4);               // W
   sz[PA_VEC] = L.vec_doubles;
   const int64_t nlist = std::max(nc, cap);
   L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);

@@ -14,6 +14,7 @@ struct Ctx
   double *Pi, *As, *Si, *G, *Y;
   double* Bt;      // [A_s; C_s]^T, n x ldb (L2 workspace)
   double* kt;      // ne + ni products of one Bt pass (shared memory)
+  double* W;       // P^-1 B^T, n x ldb (L2 workspace; only needed to form G)
   int ldb, ldn;    // leading dimensions of Bt and Pi (even)
   const double *Hs, *Cs;        // scaled matrices of this QP (global)
   const double *Hm, *Am, *Cm;   // model matrices (global, unscaled)
@@ -332,6 +333,74 @@ __device__ __forceinline__ void axpy_pass(const Ctx& c, const double* base, int 
   axpy_pass2(c, base, nrows, base, ld, nullptr, 0, nrows, coef, ncols, out, add, sign);
 }
 
+// Out[i][c] = sum_{j < K} CM[j][i] * R[j][c]   (Out = CM^T R), i < M, c < ncols.
+// All operands in the L2 workspace, row-major with even leading dimensions.
+// A warp owns four output rows at a time and streams the K rows of R once per
+// group (register tile 4 x 2*NCH per lane); the four coefficients of a step are
+// one 32-byte broadcast. Used once per QP to form W = P^-1 B^T and the Gram
+// matrix G = B W of ALL constraint rows, which turns every later active-set
+// insertion into a gather.
+template<int NCH>
+__device__ void gemm_tn_t(const double* __restrict__ CM, int ldc, const double* __restrict__ R, int ldr, int K, int M, int ncols, double* __restrict__ Out, int ldo)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int np = (ncols + 1) >> 1;
+  bool pv[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) pv[ch] = lane + 32 * ch < np;
+  _Pragma("unroll 1") for (int i0 = 4 * warp; i0 < M; i0 += 4 * NW) {
+    double2 acc[4][NCH];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) acc[r][ch] = make_double2(0.0, 0.0);
+    }
+    const double2* cp = reinterpret_cast<const double2*>(CM + i0);
+    const double2* rp = reinterpret_cast<const double2*>(R) + lane;
+    _Pragma("unroll 2") for (int j = 0; j < K; ++j) {
+      const double2 c01 = cp[(size_t)j * (ldc >> 1)];
+      const double2 c23 = cp[(size_t)j * (ldc >> 1) + 1];
+      double2 rv[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) rv[ch] = pv[ch] ? rp[(size_t)j * (ldr >> 1) + 32 * ch] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        acc[0][ch].x = fma(c01.x, rv[ch].x, acc[0][ch].x);
+        acc[0][ch].y = fma(c01.x, rv[ch].y, acc[0][ch].y);
+        acc[1][ch].x = fma(c01.y, rv[ch].x, acc[1][ch].x);
+        acc[1][ch].y = fma(c01.y, rv[ch].y, acc[1][ch].y);
+        acc[2][ch].x = fma(c23.x, rv[ch].x, acc[2][ch].x);
+        acc[2][ch].y = fma(c23.x, rv[ch].y, acc[2][ch].y);
+        acc[3][ch].x = fma(c23.y, rv[ch].x, acc[3][ch].x);
+        acc[3][ch].y = fma(c23.y, rv[ch].y, acc[3][ch].y);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (i0 + r < M) {
+        double2* op = reinterpret_cast<double2*>(Out + (size_t)(i0 + r) * ldo) + lane;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          if (pv[ch]) op[32 * ch] = acc[r][ch];
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+__device__ __noinline__ void gemm_tn(const double* CM, int ldc, const double* R, int ldr, int K, int M, int ncols, double* Out, int ldo)
+{
+  const int np = (ncols + 1) >> 1;
+  if (np <= 32)
+    gemm_tn_t<1>(CM, ldc, R, ldr, K, M, ncols, Out, ldo);
+  else if (np <= 64)
+    gemm_tn_t<2>(CM, ldc, R, ldr, K, M, ncols, Out, ldo);
+  else if (np <= 96)
+    gemm_tn_t<3>(CM, ldc, R, ldr, K, M, ncols, Out, ldo);
+  else
+    gemm_tn_t<4>(CM, ldc, R, ldr, K, M, ncols, Out, ldo);
+}
+
 // ---------------------------------------------------------------------------
 // Symmetric matrices in TILE storage (S^-1, and P during its inversion).
 // The lower triangle is cut into 32 x 32 tiles (bi, bj), bj <= bi, each stored
@@ -645,26 +714,6 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
   apply_Pinv(c, v_t2, ox);
 }
 
-// Gram row of dual slot s against slots 0..s:  y = P^-1 b_s (-> t1),
-// s3[j] = b_j . y, stored in G by row id.
-__device__ void gram_row(Ctx& c, int s)
-{
-  PQP_VECS(c);
-  const int n = c.n, ne = c.ne;
-  const double* row = (s < ne) ? c.As + (size_t)s * n : c.Cs + (size_t)c.slot_cons[s] * n;
-  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) v_t2[j] = row[j];
-  __syncthreads();
-  apply_Pinv(c, v_t2, v_t1);
-  axpy_pass(c, c.Bt, c.ldb, n, v_t1, ne + c.ni, c.kt, nullptr, 1.0);
-  const int ids = row_id(c, s);
-  _Pragma("unroll 1") for (int j = threadIdx.x; j <= s; j += NT) {
-    const double g = c.kt[row_id(c, j)];
-    v_s3[j] = g;
-    c.G[gidx(ids, row_id(c, j))] = g;
-  }
-  __syncthreads();
-}
-
 // Append dual slot s == c.ns (already registered in slot_cons) with proximal
 // parameter mu: bordering of the explicit inverse
 //   w = S^-1 g, delta = (b.P^-1 b + mu) - g.w,
@@ -680,7 +729,12 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu)
     __syncthreads();
     return;
   }
-  gram_row(c, s);
+  {
+    // Gram row of the new slot against slots 0..s: a gather from G
+    const double* grow = c.G + (size_t)row_id(c, s) * c.ldb;
+    _Pragma("unroll 1") for (int j = threadIdx.x; j <= s; j += NT) v_s3[j] = grow[row_id(c, j)];
+    __syncthreads();
+  }
   double delta = v_s3[s] + mu;
   if (s > 0) {
     tsym_mv(c, c.Si, v_s3, v_s1, s);
@@ -765,7 +819,7 @@ __device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_i
       for (int bj = 0; bj <= bi; ++bj) {
         const int t = 32 * bj + lane;
         double v = 0.0;
-        if (s < ns && t < ns) v = c.G[gidx(ids, row_id(c, t))] + ((t == s) ? (s < c.ne ? mu_eq : mu_in) : 0.0);
+        if (s < ns && t < ns) v = c.G[(size_t)ids * c.ldb + row_id(c, t)] + ((t == s) ? (s < c.ne ? mu_eq : mu_in) : 0.0);
         c.Si[ts_tile(cap, bi, bj) + r * TS_LD + lane] = v;
       }
     }
@@ -823,12 +877,20 @@ __device__ __noinline__ void build_Bt(Ctx& c)
   __syncthreads();
 }
 
+// W = P^-1 B^T and G = B W for all rows of B = [A_s; C_s] (G is symmetric; both
+// halves are formed). Depends on H_s, rho, A_s, C_s only: once per QP.
+__device__ __noinline__ void build_G(Ctx& c)
+{
+  const int n = c.n, m = c.ne + c.ni;
+  gemm_tn(c.Pi, c.ldn, c.Bt, c.ldb, n, n, m, c.W, c.ldb); // W = Pi^T Bt (Pi symmetric)
+  gemm_tn(c.Bt, c.ldb, c.W, c.ldb, n, m, m, c.G, c.ldb);  // G = Bt^T W
+}
+
 // (Re)build the dual block for the slots 0..ns_target-1 currently registered:
-// Gram rows, then one sweep inversion. Used for the first factorisation
+// gather from G, then one sweep inversion. Used for the first factorisation
 // (equality rows only, helpers.hpp:241-285) and by refactorize (solver.hpp:40-87).
 __device__ __noinline__ void build_dual_block(Ctx& c, int ns_target, double mu_eq, double mu_in)
 {
-  for (int s = 0; s < ns_target; ++s) gram_row(c, s);
   if (threadIdx.x == 0) c.ns = ns_target;
   __syncthreads();
   if (ns_target > 0) rebuild_Si_from_G(c, mu_eq, mu_in);
@@ -884,7 +946,8 @@ __device__ void refactorize(Ctx& c, Scal& sc)
   if (sc.factor_fresh) return;
   const int ns_target = c.ns;
   __syncthreads();
-  build_Pi(c, sc.rho);
+  // P^-1, W and G depend on (H_s, rho, A_s, C_s) only and carry no accumulated
+  // update error: only the incrementally updated S^-1 is rebuilt
   build_dual_block(c, ns_target, sc.mu_eq, sc.mu_in);
   sc.factor_fresh = true;
 }
@@ -1388,6 +1451,9 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
   build_Pi(c, sc.rho);
   PROF_ADD(PH_M1, tph);
   tph = PROF_T0();
+  build_G(c);
+  PROF_ADD(PH_EQ, tph);
+  tph = PROF_T0();
   build_dual_block(c, ne, sc.mu_eq, sc.mu_in);
   PROF_ADD(PH_EQ, tph);
 
@@ -1851,7 +1917,8 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArg
     c.Bt = place(PA_AS); // the A_s slot of the workspace holds Bt in this layout
     c.Si = place(PA_MS);
     c.G = place(PA_G);
-    c.Y = place(PA_Y);
+    c.Y = nullptr;
+    c.W = place(PA_Y); // the Y slot of the workspace holds W in this layout
     double* v = place(PA_VEC);
     c.x = v + L.voff[V_X];
     c.y = v + L.voff[V_Y];
