@@ -44,6 +44,12 @@ class pqp_info(C.Structure):
                 ("minimal_H_eigenvalue_estimate", C.c_double)]
 
 
+import numpy as _np  # noqa: E402
+
+# numpy view of an array of pqp_info (all members are 8 bytes wide, no padding)
+INFO_DTYPE = _np.dtype([(k, _np.int64 if t is C.c_int64 else _np.float64) for k, t in pqp_info._fields_])
+assert INFO_DTYPE.itemsize == C.sizeof(pqp_info)
+
 # every symbol include/pqp.h declares
 EXPORTED_SYMBOLS = [
     "pqp_settings_default", "pqp_dense_backend_choice", "pqp_batch_create", "pqp_batch_destroy", "pqp_batch_size",

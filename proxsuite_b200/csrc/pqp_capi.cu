@@ -46,6 +46,8 @@ struct QpFlags
 
 } // namespace
 
+#define PQP_UPLOAD_CHUNKS 8
+
 struct pqp_batch
 {
   int64_t B = 0;
@@ -58,7 +60,9 @@ struct pqp_batch
   std::vector<pqp_info> hinfo;      // results.info (host truth between solves)
   std::vector<QpFlags> flags;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr; // host->device uploads of init(), chunked so that the set-up kernels overlap them
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_chunk[PQP_UPLOAD_CHUNKS] = {};
   bool setup_timed = false, solve_timed = false;
   PqpLayout lay{};      // primary layout (fast kernel when the inverse blocks are in shared memory)
   PqpLayout lay_gen{};  // fallback: everything but the vectors in global memory, full capacity
@@ -375,10 +379,10 @@ check_range(pqp_batch* b, int64_t first, int64_t count)
 }
 
 int
-copy_in(pqp_batch* b, double* dst_base, const double* src, int64_t first, int64_t count, int64_t per_qp, bool src_is_device)
+copy_in(pqp_batch* b, double* dst_base, const double* src, int64_t first, int64_t count, int64_t per_qp, bool src_is_device, cudaStream_t st = nullptr)
 {
   if (!src || per_qp == 0 || count == 0) return 0;
-  CUDA_TRY(cudaMemcpyAsync(dst_base + first * per_qp, src, sizeof(double) * (size_t)(count * per_qp), src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(dst_base + first * per_qp, src, sizeof(double) * (size_t)(count * per_qp), src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st ? st : b->stream));
   return 0;
 }
 
@@ -421,21 +425,41 @@ update_default_rho(pqp_batch* b, int64_t i, const double* manual)
   info.rho = s.default_rho;
 }
 
+// zero x, y, z, se, si of the QPs [i, i + cnt)
 int
-zero_results(pqp_batch* b, int64_t i)
+zero_results(pqp_batch* b, int64_t i, int64_t cnt = 1)
 {
   const PqpDims& d = b->d;
-  CUDA_TRY(cudaMemsetAsync(b->p.x + i * d.n, 0, sizeof(double) * d.n, b->stream));
-  if (d.ne) CUDA_TRY(cudaMemsetAsync(b->p.y + i * d.ne, 0, sizeof(double) * d.ne, b->stream));
-  if (d.ne) CUDA_TRY(cudaMemsetAsync(b->p.se + i * d.ne, 0, sizeof(double) * d.ne, b->stream));
-  if (d.nc) CUDA_TRY(cudaMemsetAsync(b->p.z + i * d.nc, 0, sizeof(double) * d.nc, b->stream));
-  if (d.nc) CUDA_TRY(cudaMemsetAsync(b->p.si + i * d.nc, 0, sizeof(double) * d.nc, b->stream));
+  if (cnt <= 0) return 0;
+  CUDA_TRY(cudaMemsetAsync(b->p.x + i * d.n, 0, sizeof(double) * d.n * cnt, b->stream));
+  if (d.ne) CUDA_TRY(cudaMemsetAsync(b->p.y + i * d.ne, 0, sizeof(double) * d.ne * cnt, b->stream));
+  if (d.ne) CUDA_TRY(cudaMemsetAsync(b->p.se + i * d.ne, 0, sizeof(double) * d.ne * cnt, b->stream));
+  if (d.nc) CUDA_TRY(cudaMemsetAsync(b->p.z + i * d.nc, 0, sizeof(double) * d.nc * cnt, b->stream));
+  if (d.nc) CUDA_TRY(cudaMemsetAsync(b->p.si + i * d.nc, 0, sizeof(double) * d.nc * cnt, b->stream));
+  return 0;
+}
+// the same for the QPs flagged in need[0 .. count): one memset per array and contiguous run
+int
+zero_results_runs(pqp_batch* b, int64_t first, const std::vector<char>& need)
+{
+  const int64_t count = (int64_t)need.size();
+  int64_t k = 0;
+  while (k < count) {
+    if (!need[k]) {
+      ++k;
+      continue;
+    }
+    int64_t e = k;
+    while (e < count && need[e]) ++e;
+    if (int rc = zero_results(b, first + k, e - k)) return rc;
+    k = e;
+  }
   return 0;
 }
 
 // helpers.hpp:522-572: what setup() does to results / workspace flags
 int
-setup_results_and_flags(pqp_batch* b, int64_t i)
+setup_results_and_flags(pqp_batch* b, int64_t i, char* need_zero = nullptr)
 {
   pqp_settings& s = b->hparams[i].s;
   pqp_info& info = b->hinfo[i];
@@ -446,7 +470,10 @@ setup_results_and_flags(pqp_batch* b, int64_t i)
     case PQP_NO_INITIAL_GUESS:
     case PQP_WARM_START: {
       bool ppu = f.proximal_parameter_update;
-      if (int rc = zero_results(b, i)) return rc;
+      if (need_zero)
+        *need_zero = 1; // the caller zeroes whole runs of QPs with one memset per array
+      else if (int rc = zero_results(b, i))
+        return rc;
       if (ppu)
         cleanup_statistics(info);
       else
@@ -474,7 +501,7 @@ setup_results_and_flags(pqp_batch* b, int64_t i)
 }
 
 int
-launch_setup(pqp_batch* b, int64_t first, int64_t count, bool execute, bool reset_scaling)
+launch_setup(pqp_batch* b, int64_t first, int64_t count, bool execute, bool reset_scaling, bool time_begin = true, bool time_end = true)
 {
   // device needs the settings (preconditioner parameters) of these QPs
   CUDA_TRY(cudaMemcpyAsync(b->p.params + first, b->hparams.data() + first, sizeof(PqpQpParams) * (size_t)count, cudaMemcpyHostToDevice, b->stream));
@@ -485,10 +512,10 @@ launch_setup(pqp_batch* b, int64_t first, int64_t count, bool execute, bool rese
   a.count = (int32_t)count;
   a.execute = execute ? 1 : 0;
   a.reset_scaling = reset_scaling ? 1 : 0;
-  CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
+  if (time_begin) CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
   int rc = pqp_launch_setup(&a, b->stream);
   if (rc != 0) return fail(PQP_ECUDA, std::string("setup kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
-  CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+  if (time_end) CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
   b->setup_timed = true;
   b->launches += 1;
   return 0;
@@ -503,6 +530,7 @@ do_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const doubl
   if (!d.box && (l_box || u_box))
     return fail(PQP_EINVAL, "wrong model setup: the QP object is designed without box constraints, but is initialized with lower or upper box inequalities.");
   CUDA_TRY(cudaSetDevice(b->device));
+  std::vector<char> need_zero((size_t)count, 0);
   for (int64_t i = first; i < first + count; ++i) {
     pqp_settings& s = b->hparams[i].s;
     QpFlags& f = b->flags[i];
@@ -511,22 +539,40 @@ do_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const doubl
     f.proximal_parameter_update = false;
     update_proximal_parameters(b, i, rho, mu_eq, mu_in);
     update_default_rho(b, i, manual_eig);
-    if (int rc = setup_results_and_flags(b, i)) return rc;
+    if (int rc = setup_results_and_flags(b, i, &need_zero[(size_t)(i - first)])) return rc;
     f.is_initialized = true;
   }
+  if (int rc = zero_results_runs(b, first, need_zero)) return rc;
   const int64_t n = d.n, ne = d.ne, ni = d.ni;
-  if (int rc = copy_in(b, b->p.H, H, first, count, n * n, dev_ptrs)) return rc;
-  if (int rc = copy_in(b, b->p.g, g, first, count, n, dev_ptrs)) return rc;
-  if (int rc = copy_in(b, b->p.A, A, first, count, ne * n, dev_ptrs)) return rc;
-  if (int rc = copy_in(b, b->p.b, b_, first, count, ne, dev_ptrs)) return rc;
-  if (int rc = copy_in(b, b->p.C, C, first, count, ni * n, dev_ptrs)) return rc;
-  if (int rc = copy_in(b, b->p.l, l, first, count, ni, dev_ptrs)) return rc;
-  if (int rc = copy_in(b, b->p.u, u, first, count, ni, dev_ptrs)) return rc;
-  if (d.box) {
-    if (int rc = copy_in(b, b->p.l_box, l_box, first, count, n, dev_ptrs)) return rc;
-    if (int rc = copy_in(b, b->p.u_box, u_box, first, count, n, dev_ptrs)) return rc;
+  // Host inputs of a large range are uploaded in chunks on a second stream; the set-up kernel of
+  // chunk k runs while chunk k+1 is still crossing PCIe.
+  const int nchunks = (!dev_ptrs && count >= 256) ? (int)std::min<int64_t>(PQP_UPLOAD_CHUNKS, count / 128) : 1;
+  if (nchunks > 1) {
+    CUDA_TRY(cudaEventRecord(b->ev_main, b->stream)); // uploads must not overtake kernels still reading the buffers
+    CUDA_TRY(cudaStreamWaitEvent(b->copy_stream, b->ev_main, 0));
   }
-  return launch_setup(b, first, count, compute_preconditioner != 0, compute_preconditioner == 0);
+  for (int k = 0; k < nchunks; ++k) {
+    const int64_t f = first + count * k / nchunks, e = first + count * (k + 1) / nchunks, cnt = e - f, o = f - first;
+    cudaStream_t st = nchunks > 1 ? b->copy_stream : b->stream;
+    auto at = [&](const double* src, int64_t per) { return src ? src + o * per : nullptr; };
+    if (int rc = copy_in(b, b->p.H, at(H, n * n), f, cnt, n * n, dev_ptrs, st)) return rc;
+    if (int rc = copy_in(b, b->p.g, at(g, n), f, cnt, n, dev_ptrs, st)) return rc;
+    if (int rc = copy_in(b, b->p.A, at(A, ne * n), f, cnt, ne * n, dev_ptrs, st)) return rc;
+    if (int rc = copy_in(b, b->p.b, at(b_, ne), f, cnt, ne, dev_ptrs, st)) return rc;
+    if (int rc = copy_in(b, b->p.C, at(C, ni * n), f, cnt, ni * n, dev_ptrs, st)) return rc;
+    if (int rc = copy_in(b, b->p.l, at(l, ni), f, cnt, ni, dev_ptrs, st)) return rc;
+    if (int rc = copy_in(b, b->p.u, at(u, ni), f, cnt, ni, dev_ptrs, st)) return rc;
+    if (d.box) {
+      if (int rc = copy_in(b, b->p.l_box, at(l_box, n), f, cnt, n, dev_ptrs, st)) return rc;
+      if (int rc = copy_in(b, b->p.u_box, at(u_box, n), f, cnt, n, dev_ptrs, st)) return rc;
+    }
+    if (nchunks > 1) {
+      CUDA_TRY(cudaEventRecord(b->ev_chunk[k], b->copy_stream));
+      CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_chunk[k], 0));
+    }
+    if (int rc = launch_setup(b, f, cnt, compute_preconditioner != 0, compute_preconditioner == 0, k == 0, k == nchunks - 1)) return rc;
+  }
+  return 0;
 }
 
 void
@@ -732,7 +778,9 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
     info_defaults(b->hinfo[i], nullptr, b->backend);
     b->hinfo[i].status = PQP_NOT_RUN;
   }
-  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess || cudaEventCreate(&b->ev2) != cudaSuccess ||
+  bool aux_ok = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < PQP_UPLOAD_CHUNKS; ++k) aux_ok = aux_ok && cudaEventCreateWithFlags(&b->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
+  if (!aux_ok || cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess || cudaEventCreate(&b->ev2) != cudaSuccess ||
       cudaEventCreate(&b->ev3) != cudaSuccess) {
     fail(PQP_ECUDA, "stream/event creation failed");
     pqp_batch_destroy(b);
@@ -774,12 +822,17 @@ pqp_batch_destroy(pqp_batch* b)
 {
   if (!b) return;
   cudaSetDevice(b->device);
+  if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (void* p : b->allocs) cudaFree(p);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->ev2) cudaEventDestroy(b->ev2);
   if (b->ev3) cudaEventDestroy(b->ev3);
+  if (b->ev_main) cudaEventDestroy(b->ev_main);
+  for (int k = 0; k < PQP_UPLOAD_CHUNKS; ++k)
+    if (b->ev_chunk[k]) cudaEventDestroy(b->ev_chunk[k]);
+  if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -852,6 +905,7 @@ pqp_batch_update(pqp_batch* b, int64_t first, int64_t count, const double* H, co
   }
   if (none_init && count > 0) return do_init(b, first, count, H, g, A, b_, C, l, u, l_box, u_box, update_preconditioner, rho, mu_eq, mu_in, nullptr, false);
   if (!all_init) return fail(PQP_ESTATE, "update on a range that mixes initialised and non-initialised QPs");
+  std::vector<char> need_zero((size_t)count, 0);
   for (int64_t i = first; i < first + count; ++i) {
     pqp_settings& s = b->hparams[i].s;
     QpFlags& f = b->flags[i];
@@ -861,12 +915,13 @@ pqp_batch_update(pqp_batch* b, int64_t first, int64_t count, const double* H, co
     if (H || A || C) f.refactorize = true; // helpers.hpp:466-468
     update_proximal_parameters(b, i, rho, mu_eq, mu_in);
     update_default_rho(b, i, manual_eig);
-    if (int rc = setup_results_and_flags(b, i)) return rc;
+    if (int rc = setup_results_and_flags(b, i, &need_zero[(size_t)(i - first)])) return rc;
     // Workspace::cleanup clears is_initialized (workspace.hpp:330-377); the
     // reference only re-sets it in qp_solve. Model data stay valid, so the
     // batch keeps the QP solvable.
     f.is_initialized = true;
   }
+  if (int rc = zero_results_runs(b, first, need_zero)) return rc;
   const int64_t n = d.n, ne = d.ne, ni = d.ni;
   if (int rc = copy_in(b, b->p.H, H, first, count, n * n, false)) return rc;
   if (int rc = copy_in(b, b->p.g, g, first, count, n, false)) return rc;
@@ -1094,8 +1149,8 @@ pqp_batch_cleanup(pqp_batch* b, int64_t first, int64_t count)
 {
   if (int rc = check_range(b, first, count)) return rc;
   CUDA_TRY(cudaSetDevice(b->device));
+  if (int rc = zero_results(b, first, count)) return rc;
   for (int64_t i = first; i < first + count; ++i) {
-    if (int rc = zero_results(b, i)) return rc;
     cold_start(b->hinfo[i], &b->hparams[i].s, b->backend);
     b->flags[i] = QpFlags(); // workspace.hpp:330-377
   }

@@ -244,7 +244,7 @@ __device__ __forceinline__ void reduce_rows(double (&d)[RR], int lane)
 template<int NCH>
 __device__ void axpy_pass_t(const Ctx& c, const double* __restrict__ base0, int split, const double* __restrict__ base1, int ld, const int* __restrict__ list, int byid, int nrows, const double* __restrict__ coef, int ncols, double* out, const double* add, double sign)
 {
-  constexpr int UNR = (NCH <= 2) ? 4 : 2;
+  constexpr int UNR = (NCH <= 2) ? 8 : 4; // rows in flight per warp (L2 latency is the bound)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* const scr = c.scratch;
   PQP_SM(scr);
@@ -333,72 +333,64 @@ __device__ __forceinline__ void axpy_pass(const Ctx& c, const double* base, int 
   axpy_pass2(c, base, nrows, base, ld, nullptr, 0, nrows, coef, ncols, out, add, sign);
 }
 
-// Out[i][c] = sum_{j < K} CM[j][i] * R[j][c]   (Out = CM^T R), i < M, c < ncols.
-// All operands in the L2 workspace, row-major with even leading dimensions.
-// A warp owns four output rows at a time and streams the K rows of R once per
-// group (register tile 4 x 2*NCH per lane); the four coefficients of a step are
-// one 32-byte broadcast. Used once per QP to form W = P^-1 B^T and the Gram
-// matrix G = B W of ALL constraint rows, which turns every later active-set
-// insertion into a gather.
-template<int NCH>
-__device__ void gemm_tn_t(const double* __restrict__ CM, int ldc, const double* __restrict__ R, int ldr, int K, int M, int ncols, double* __restrict__ Out, int ldo)
+// Out[i][c] = sum_{k < K} CM[k][i] * R[k][c]   (Out = CM^T R), i < M, c < ncols,
+// on the FP64 tensor cores (mma.sync m8n8k4, the one dense contraction of this
+// path). All operands live in the L2 workspace, row-major with even leading
+// dimensions. A warp owns a 16 x 32 output tile (2 x 4 MMA tiles); both operand
+// fragments have the same access shape (row k0 + lane%4, column base + lane/4),
+// so no staging or transposition is needed. `lower` skips the tiles strictly
+// above the block diagonal (symmetric result, read as [max][min]).
+// Used once per QP to form W = P^-1 B^T and the Gram matrix G = B W of ALL
+// constraint rows, which turns every active-set insertion into a gather.
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __noinline__ void gemm_tn(const double* __restrict__ CM, int ldc, const double* __restrict__ R, int ldr, int K, int M, int ncols, double* __restrict__ Out, int ldo, bool lower)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int np = (ncols + 1) >> 1;
-  bool pv[NCH];
+  const int g = lane >> 2, t = lane & 3;
+  const int mb = (M + 15) >> 4, nbk = (ncols + 31) >> 5;
+  _Pragma("unroll 1") for (int tile = warp; tile < mb * nbk; tile += NW) {
+    const int i0 = (tile / nbk) << 4, c0 = (tile % nbk) << 5;
+    if (lower && c0 > i0 + 15) continue;
+    double acc[2][4][2];
 #pragma unroll
-  for (int ch = 0; ch < NCH; ++ch) pv[ch] = lane + 32 * ch < np;
-  _Pragma("unroll 1") for (int i0 = 4 * warp; i0 < M; i0 += 4 * NW) {
-    double2 acc[4][NCH];
+    for (int u = 0; u < 2; ++u) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) acc[r][ch] = make_double2(0.0, 0.0);
+      for (int j = 0; j < 4; ++j) acc[u][j][0] = acc[u][j][1] = 0.0;
     }
-    const double2* cp = reinterpret_cast<const double2*>(CM + i0);
-    const double2* rp = reinterpret_cast<const double2*>(R) + lane;
-    _Pragma("unroll 2") for (int j = 0; j < K; ++j) {
-      const double2 c01 = cp[(size_t)j * (ldc >> 1)];
-      const double2 c23 = cp[(size_t)j * (ldc >> 1) + 1];
-      double2 rv[NCH];
+    bool av[2], bv[4];
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) rv[ch] = pv[ch] ? rp[(size_t)j * (ldr >> 1) + 32 * ch] : make_double2(0.0, 0.0);
+    for (int u = 0; u < 2; ++u) av[u] = i0 + 8 * u + g < M;
 #pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        acc[0][ch].x = fma(c01.x, rv[ch].x, acc[0][ch].x);
-        acc[0][ch].y = fma(c01.x, rv[ch].y, acc[0][ch].y);
-        acc[1][ch].x = fma(c01.y, rv[ch].x, acc[1][ch].x);
-        acc[1][ch].y = fma(c01.y, rv[ch].y, acc[1][ch].y);
-        acc[2][ch].x = fma(c23.x, rv[ch].x, acc[2][ch].x);
-        acc[2][ch].y = fma(c23.x, rv[ch].y, acc[2][ch].y);
-        acc[3][ch].x = fma(c23.y, rv[ch].x, acc[3][ch].x);
-        acc[3][ch].y = fma(c23.y, rv[ch].y, acc[3][ch].y);
+    for (int j = 0; j < 4; ++j) bv[j] = c0 + 8 * j + g < ncols;
+    const double* ap = CM + (size_t)t * ldc + i0 + g;
+    const double* bp = R + (size_t)t * ldr + c0 + g;
+    _Pragma("unroll 2") for (int k0 = 0; k0 < K; k0 += 4) {
+      const bool kv = k0 + t < K;
+      double a[2], b[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) a[u] = (av[u] && kv) ? ap[(size_t)k0 * ldc + 8 * u] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = (bv[j] && kv) ? bp[(size_t)k0 * ldr + 8 * j] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[u][j][0], acc[u][j][1], a[u], b[j]);
       }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      if (i0 + r < M) {
-        double2* op = reinterpret_cast<double2*>(Out + (size_t)(i0 + r) * ldo) + lane;
+    for (int u = 0; u < 2; ++u) {
+      const int row = i0 + 8 * u + g;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) {
-          if (pv[ch]) op[32 * ch] = acc[r][ch];
-        }
+      for (int j = 0; j < 4; ++j) {
+        const int col = c0 + 8 * j + 2 * t;
+        if (row < M && col < ncols) *reinterpret_cast<double2*>(Out + (size_t)row * ldo + col) = make_double2(acc[u][j][0], acc[u][j][1]);
       }
     }
   }
   __syncthreads();
-}
-__device__ __noinline__ void gemm_tn(const double* CM, int ldc, const double* R, int ldr, int K, int M, int ncols, double* Out, int ldo)
-{
-  const int np = (ncols + 1) >> 1;
-  if (np <= 32)
-    gemm_tn_t<1>(CM, ldc, R, ldr, K, M, ncols, Out, ldo);
-  else if (np <= 64)
-    gemm_tn_t<2>(CM, ldc, R, ldr, K, M, ncols, Out, ldo);
-  else if (np <= 96)
-    gemm_tn_t<3>(CM, ldc, R, ldr, K, M, ncols, Out, ldo);
-  else
-    gemm_tn_t<4>(CM, ldc, R, ldr, K, M, ncols, Out, ldo);
 }
 
 // ---------------------------------------------------------------------------
@@ -731,8 +723,11 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu)
   }
   {
     // Gram row of the new slot against slots 0..s: a gather from G
-    const double* grow = c.G + (size_t)row_id(c, s) * c.ldb;
-    _Pragma("unroll 1") for (int j = threadIdx.x; j <= s; j += NT) v_s3[j] = grow[row_id(c, j)];
+    const int ids = row_id(c, s);
+    _Pragma("unroll 1") for (int j = threadIdx.x; j <= s; j += NT) {
+      const int idj = row_id(c, j);
+      v_s3[j] = c.G[(size_t)max(ids, idj) * c.ldb + min(ids, idj)];
+    }
     __syncthreads();
   }
   double delta = v_s3[s] + mu;
@@ -819,7 +814,10 @@ __device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_i
       for (int bj = 0; bj <= bi; ++bj) {
         const int t = 32 * bj + lane;
         double v = 0.0;
-        if (s < ns && t < ns) v = c.G[(size_t)ids * c.ldb + row_id(c, t)] + ((t == s) ? (s < c.ne ? mu_eq : mu_in) : 0.0);
+        if (s < ns && t < ns) {
+          const int idt = row_id(c, t);
+          v = c.G[(size_t)max(ids, idt) * c.ldb + min(ids, idt)] + ((t == s) ? (s < c.ne ? mu_eq : mu_in) : 0.0);
+        }
         c.Si[ts_tile(cap, bi, bj) + r * TS_LD + lane] = v;
       }
     }
@@ -877,13 +875,13 @@ __device__ __noinline__ void build_Bt(Ctx& c)
   __syncthreads();
 }
 
-// W = P^-1 B^T and G = B W for all rows of B = [A_s; C_s] (G is symmetric; both
-// halves are formed). Depends on H_s, rho, A_s, C_s only: once per QP.
+// W = P^-1 B^T and G = B W for all rows of B = [A_s; C_s] (G is symmetric; it is
+// read as G[max][min]). Depends on H_s, rho, A_s, C_s only: once per QP.
 __device__ __noinline__ void build_G(Ctx& c)
 {
   const int n = c.n, m = c.ne + c.ni;
-  gemm_tn(c.Pi, c.ldn, c.Bt, c.ldb, n, n, m, c.W, c.ldb); // W = Pi^T Bt (Pi symmetric)
-  gemm_tn(c.Bt, c.ldb, c.W, c.ldb, n, m, m, c.G, c.ldb);  // G = Bt^T W
+  gemm_tn(c.Pi, c.ldn, c.Bt, c.ldb, n, n, m, c.W, c.ldb, false); // W = Pi^T Bt (Pi symmetric)
+  gemm_tn(c.Bt, c.ldb, c.W, c.ldb, n, m, m, c.G, c.ldb, true);   // G = Bt^T W, lower block triangle
 }
 
 // (Re)build the dual block for the slots 0..ns_target-1 currently registered:
@@ -1010,14 +1008,34 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
   PROF_ADD(PH_DELETE, tp);
   tp = PROF_T0();
   int nadd = block_compact(c, c.nc, c.list1, [&](int i) { return (c.act_up[i] || c.act_low[i]) && c.cons_slot[i] < 0; });
-  for (int k = 0; k < nadd; ++k) {
-    if (threadIdx.x == 0) {
-      int cons = c.list1[k];
-      c.slot_cons[c.ns] = cons;
-      c.cons_slot[cons] = c.ns;
+  // A bordering step costs two passes over S^-1; a rebuild from G costs (ns+nadd)/4 block
+  // sweeps of the same size. Many simultaneous additions (the first Newton steps) are
+  // therefore registered at once and S^-1 is re-formed from the Gram matrix.
+  if (nadd >= 8 && 2 * nadd >= (c.ns + nadd + 3) / 4) {
+    if (c.ns + nadd > c.si_cap) {
+      if (threadIdx.x == 0) c.overflow = 1;
+      __syncthreads();
+    } else {
+      const int base = c.ns;
+      _Pragma("unroll 1") for (int k = threadIdx.x; k < nadd; k += NT) {
+        const int cons = c.list1[k];
+        c.slot_cons[base + k] = cons;
+        c.cons_slot[cons] = base + k;
+      }
+      if (threadIdx.x == 0) c.ns = base + nadd;
+      __syncthreads();
+      rebuild_Si_from_G(c, sc.mu_eq, sc.mu_in);
     }
-    __syncthreads();
-    insert_slot(c, sc.mu_in);
+  } else {
+    for (int k = 0; k < nadd; ++k) {
+      if (threadIdx.x == 0) {
+        int cons = c.list1[k];
+        c.slot_cons[c.ns] = cons;
+        c.cons_slot[cons] = c.ns;
+      }
+      __syncthreads();
+      insert_slot(c, sc.mu_in);
+    }
   }
   PROF_ADD(PH_INSERT, tp);
   if (ndel > 0 || nadd > 0) sc.factor_fresh = false;

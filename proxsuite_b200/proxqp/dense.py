@@ -120,11 +120,11 @@ class _Group:
         self.pull_all()
 
     def fetch(self, first, count):
-        x = np.zeros((count, self.n))
-        y = np.zeros((count, self.n_eq))
-        z = np.zeros((count, self.nc))
-        se = np.zeros((count, self.n_eq))
-        si = np.zeros((count, self.nc))
+        x = np.empty((count, self.n))
+        y = np.empty((count, self.n_eq))
+        z = np.empty((count, self.nc))
+        se = np.empty((count, self.n_eq))
+        si = np.empty((count, self.nc))
         info = (_capi.pqp_info * count)()
         _capi.check(self.lib.pqp_batch_results(self.handle, first, count, _ptr(x), _ptr(y), _ptr(z), _ptr(se), _ptr(si), ct.cast(info, _VP)))
         return x, y, z, se, si, info
@@ -436,6 +436,7 @@ class DenseBatch:
                 chk(u_box, (B, n), "u_box")]
         keep = [_opt_scalar(v) for v in (rho, mu_eq, mu_in, manual_minimal_H_eigenvalue)]
         self._push()
+        self._inputs_in_flight = arrs  # pinned inputs are uploaded asynchronously: keep them alive until the next call
         fn = G.lib.pqp_batch_update if update else G.lib.pqp_batch_init
         _capi.check(fn(G.handle, 0, B, *[_ptr(a) for a in arrs], int(compute_preconditioner), *[k[1] for k in keep]))
         _capi.check(G.lib.pqp_batch_settings_get(G.handle, 0, ct.byref(self.settings._c)))
@@ -467,8 +468,9 @@ class DenseBatch:
 
     def results(self):
         x, y, z, se, si, info = self._g.fetch(0, self.batch)
-        fields = [k for k, _ in _capi.pqp_info._fields_]
-        inf = {k: np.array([getattr(info[i], k) for i in range(self.batch)]) for k in fields}
+        # one structured view over the C array instead of batch x fields attribute reads
+        rec = np.frombuffer(info, dtype=_capi.INFO_DTYPE, count=self.batch)
+        inf = {k: np.ascontiguousarray(rec[k]) for k in rec.dtype.names}
         return dict(x=x, y=y, z=z, se=se, si=si, info=inf)
 
     def timings(self):
