@@ -494,7 +494,9 @@ __device__ __noinline__ void tsym_mv(const Ctx& c, const double* __restrict__ T,
   __syncthreads();
 }
 
-// T[i][j] += u_i v_j on every stored element with i, j < n (u, v in shared memory)
+// T[i][j] += u_i v_j on every stored element with i, j < n (u, v in shared memory).
+// In a diagonal tile the upper half is computed with the operands of its mirror
+// element (u_j v_i for j > i), so the two stored halves stay bit-identical.
 __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, const double* __restrict__ u, const double* __restrict__ v, int n)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -515,12 +517,14 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
     if (bi < nb) {
       const int rows = min(32, n - 32 * bi);
       if (r0 < rows) {
-        double ur[RPB];
+        double ur[RPB], vr[RPB];
 #pragma unroll
         for (int r = 0; r < RPB; ++r) {
           const int i = 32 * bi + r0 + r;
           ur[r] = (i < n) ? u[i] : 0.0;
+          vr[r] = (i < n) ? v[i] : 0.0;
         }
+        const double ul = (32 * bi + lane < n) ? u[32 * bi + lane] : 0.0;
 #pragma unroll
         for (int bj = 0; bj <= bi; ++bj) {
           double* tile = T + ts_tile(cap, bi, bj);
@@ -529,7 +533,14 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
           for (int r = 0; r < RPB; ++r) a[r] = (r0 + r < rows) ? tile[(r0 + r) * TS_LD + lane] : 0.0;
 #pragma unroll
           for (int r = 0; r < RPB; ++r) {
-            if (r0 + r < rows) tile[(r0 + r) * TS_LD + lane] = fma(ur[r], vl[bj], a[r]);
+            if (r0 + r < rows) {
+              double val = fma(ur[r], vl[bj], a[r]);
+              if (bj == bi) {
+                const double mir = fma(ul, vr[r], a[r]);
+                val = (lane <= r0 + r) ? val : mir;
+              }
+              tile[(r0 + r) * TS_LD + lane] = val;
+            }
           }
         }
       }
@@ -539,7 +550,7 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
 }
 
 // T[i][j] += sum_k U[i][k] V[k][j], k = 0..3 in order. U is stored row-interleaved
-// (4 doubles per row i), V as four vectors of stride ldv.
+// (4 doubles per row i), V as four vectors of stride ldv. Diagonal tiles: as above.
 __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -561,6 +572,12 @@ __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, co
     if (bi < nb) {
       const int rows = min(32, n - 32 * bi);
       if (r0 < rows) {
+        // this lane's own U row of the block (operands of the mirrored half of the diagonal tile)
+        double2 la = make_double2(0.0, 0.0), lb = la;
+        if (32 * bi + lane < n) {
+          la = reinterpret_cast<const double2*>(U)[2 * (32 * bi + lane)];
+          lb = reinterpret_cast<const double2*>(U)[2 * (32 * bi + lane) + 1];
+        }
 #pragma unroll
         for (int r = 0; r < RPB; ++r) {
           if (r0 + r < rows) {
@@ -571,7 +588,10 @@ __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, co
 #pragma unroll
             for (int bj = 0; bj <= bi; ++bj) a[bj] = T[ts_tile(cap, bi, bj) + (r0 + r) * TS_LD + lane];
 #pragma unroll
-            for (int bj = 0; bj <= bi; ++bj) T[ts_tile(cap, bi, bj) + (r0 + r) * TS_LD + lane] = fma(ub.y, vl[3][bj], fma(ub.x, vl[2][bj], fma(ua.y, vl[1][bj], fma(ua.x, vl[0][bj], a[bj]))));
+            for (int bj = 0; bj < bi; ++bj) T[ts_tile(cap, bi, bj) + (r0 + r) * TS_LD + lane] = fma(ub.y, vl[3][bj], fma(ub.x, vl[2][bj], fma(ua.y, vl[1][bj], fma(ua.x, vl[0][bj], a[bj]))));
+            const double low = fma(ub.y, vl[3][bi], fma(ub.x, vl[2][bi], fma(ua.y, vl[1][bi], fma(ua.x, vl[0][bi], a[bi]))));
+            const double mir = fma(lb.y, V[3 * ldv + i], fma(lb.x, V[2 * ldv + i], fma(la.y, V[ldv + i], fma(la.x, V[i], a[bi]))));
+            T[ts_tile(cap, bi, bi) + (r0 + r) * TS_LD + lane] = (lane <= r0 + r) ? low : mir;
           }
         }
       }
@@ -599,64 +619,92 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
   PQP_SM(T);
   PQP_SM(uv);
   const int cap = c.si_cap;
-  double* const U = uv;           // [n][4]
-  double* const V = uv + 4 * ldv; // [4][ldv]
+  double* const U = uv;            // [n][4]
+  double* const V = uv + 4 * ldv;  // [4][ldv]
+  double* const tab = c.red;       // inv[4] | vK[4][4] | final pivot block [4][4]
+  PQP_SM(tab);
+  const int i = threadIdx.x;
   for (int k0 = 0; k0 < n; k0 += 4) {
     const int kb = min(4, n - k0);
-    double a[4][4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) a[q][r] = (q < kb && r < kb) ? ts_get(T, cap, k0 + q, k0 + r) : ((q == r) ? 1.0 : 0.0);
-    }
-    const int i = threadIdx.x;
-    double p[4], ui[4], vi[4];
     const int ai = i - k0; // position of this row inside the pivot block when 0 <= ai < kb
     const bool inK = (ai >= 0) && (ai < kb);
-    if (i < n) {
+    // positions of the panel entries (i, k0 .. k0+3): row form (valid when block(k0) <= block(i)),
+    // column form (valid when block(i) <= block(k0)); both inside a diagonal tile
+    const bool rowv = (k0 >> 5) <= (i >> 5), colv = (i >> 5) <= (k0 >> 5);
+    const int rowpos = rowv ? ts_idx(cap, i, k0) : 0;
+    const int colpos = colv ? ts_idx(cap, k0, i) : 0;
+    double p[4] = { 0.0, 0.0, 0.0, 0.0 };
+    if (i < n && !inK) {
 #pragma unroll
-      for (int l = 0; l < 4; ++l) p[l] = (l < kb) ? ts_get(T, cap, i, k0 + l) : 0.0;
+      for (int l = 0; l < 4; ++l) {
+        if (l < kb) p[l] = rowv ? T[rowpos + l] : T[colpos + TS_LD * l];
+      }
     }
-    __syncthreads(); // every thread holds the pivot block and its panel row before anything is overwritten
-    if (i < n) {
+    if (threadIdx.x < 32) {
+      // warp 0 sweeps the (identity padded) pivot block and publishes, per pivot, 1/d and the
+      // scaled pivot row, plus the finished block
+      const int pb = ts_idx(cap, k0, k0);
+      double a[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[q][r] = (q < kb && r < kb) ? T[pb + TS_LD * q + r] : ((q == r) ? 1.0 : 0.0);
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (k < kb) {
-          const double inv = 1.0 / a[k][k];
-          double vK[4];
+        const double inv = 1.0 / a[k][k];
+        double vK[4];
 #pragma unroll
-          for (int l = 0; l < 4; ++l) vK[l] = -a[k][l] * inv;
-          const double pk = p[k];
-          if (ai == k) {
-            ui[k] = 0.0;
-            vi[k] = 0.0;
+        for (int l = 0; l < 4; ++l) vK[l] = -a[k][l] * inv;
+        if (threadIdx.x == 0) {
+          tab[k] = inv;
 #pragma unroll
-            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? -inv : p[l] * inv;
-          } else {
-            ui[k] = inK ? 0.0 : pk;
-            vi[k] = inK ? 0.0 : -pk * inv;
-#pragma unroll
-            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? pk * inv : fma(pk, vK[l], p[l]);
-          }
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            if (m != k) {
-              const double amk = a[m][k];
-#pragma unroll
-              for (int l = 0; l < 4; ++l) a[m][l] = (l == k) ? amk * inv : fma(amk, vK[l], a[m][l]);
-            }
-          }
-#pragma unroll
-          for (int l = 0; l < 4; ++l) a[k][l] = (l == k) ? -inv : a[k][l] * inv;
-        } else {
-          ui[k] = 0.0;
-          vi[k] = 0.0;
+          for (int l = 0; l < 4; ++l) tab[4 + 4 * k + l] = vK[l];
         }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (m != k) {
+            const double amk = a[m][k];
+#pragma unroll
+            for (int l = 0; l < 4; ++l) a[m][l] = (l == k) ? amk * inv : fma(amk, vK[l], a[m][l]);
+          }
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) a[k][l] = (l == k) ? -inv : a[k][l] * inv;
+      }
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) tab[20 + 4 * q + r] = a[q][r];
+        }
+      }
+    }
+    __syncthreads(); // table published; every panel row has been read
+    if (i < n) {
+      double ui[4] = { 0.0, 0.0, 0.0, 0.0 }, vi[4] = { 0.0, 0.0, 0.0, 0.0 };
+      if (!inK) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < kb) {
+            const double inv = tab[k];
+            const double pk = p[k];
+            ui[k] = pk;
+            vi[k] = -pk * inv;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? pk * inv : fma(pk, tab[4 + 4 * k + l], p[l]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) p[l] = tab[20 + 4 * ai + l]; // finished pivot row
       }
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
-        const int col = k0 + l;
-        if (l < kb && (i >= col || !inK)) ts_put(T, cap, i, col, p[l]);
+        if (l < kb) {
+          if (rowv) T[rowpos + l] = p[l];
+          if (colv && !inK) T[colpos + TS_LD * l] = p[l];
+        }
         V[l * ldv + i] = vi[l];
       }
       reinterpret_cast<double2*>(U)[2 * i] = make_double2(ui[0], ui[1]);
@@ -843,7 +891,7 @@ __device__ __noinline__ void build_Pi(Ctx& c, double rho)
       for (int bj = 0; bj <= bi; ++bj) {
         const int j = 32 * bj + lane;
         double v = 0.0;
-        if (i < n && j < n) v = c.Hs[(size_t)i * n + j] + ((j == i) ? rho : 0.0);
+        if (i < n && j < n) v = c.Hs[(size_t)max(i, j) * n + min(i, j)] + ((j == i) ? rho : 0.0); // lower triangle of H_s, mirrored
         work[ts_tile(cap, bi, bj) + r * TS_LD + lane] = v;
       }
     }
