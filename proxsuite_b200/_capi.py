@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpqp_b200.so")
+LIB_PATH = os.environ.get("PQP_B200_LIB") or os.path.join(_HERE, "libpqp_b200.so")
 
 PQP_OK, PQP_EINVAL, PQP_ECUDA, PQP_ESTATE = 0, -1, -2, -3
 

@@ -222,7 +222,7 @@ tile_doubles(int64_t cap)
 // Tile layout (kind 1) of the specialised kernel: vectors + S^-1 (tile storage, capacity
 // si_cap <= 128) in shared memory; P^-1 (n x ldn), Bt (n x ldb) and G in the per-CTA workspace.
 int
-fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_cap, int ctas)
+fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_cap, int ctas, bool pi_smem = false)
 {
   std::memset(&L, 0, sizeof(L));
   const int n = d.n, ne = d.ne, nc = d.nc, cap = d.cap;
@@ -282,13 +282,13 @@ fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_ca
   };
   put(PA_VEC, true);
   put(PA_MS, true);
-  put(PA_M1, false);
+  put(PA_M1, pi_smem);
   put(PA_AS, false);
   put(PA_G, false);
   put(PA_Y, false);
   L.smem_doubles = (int32_t)smem_d;
   L.ws_doubles = std::max<int64_t>(ws_d, 2);
-  return (L.in_smem[PA_VEC] && L.in_smem[PA_MS]) ? 0 : 1;
+  return (L.in_smem[PA_VEC] && L.in_smem[PA_MS] && (!pi_smem || L.in_smem[PA_M1])) ? 0 : 1;
 }
 
 int64_t
@@ -313,11 +313,15 @@ make_layout(pqp_batch* b)
   bool done = false;
   // tile layout (specialised kernel): dense Hessian, no box constraints, n even and <= 128
   if ((m == "auto" || m == "tile") && d.hess == PQP_HESSIAN_DENSE && !d.box && (d.n % 2) == 0 && d.n <= 128 && d.n >= 2 && d.ne + d.ni <= 254 && d.nc > 0) {
-    const int64_t per_cta = ((int64_t)smem_sm - 2 * 1024) / 2;
+    // experiment hook: PQP_TILE_CTAS=1 -> one CTA per SM with P^-1 in shared memory as well
+    const char* tce = std::getenv("PQP_TILE_CTAS");
+    const int tctas = (tce && std::atoi(tce) == 1) ? 1 : 2;
+    const bool pis = tctas == 1;
+    const int64_t per_cta = tctas == 1 ? (int64_t)max_smem : ((int64_t)smem_sm - 2 * 1024) / 2;
     int best = 0;
     for (int cnd = std::min(std::max(d.cap, d.n), 128); cnd >= std::max(d.n, d.ne + 1); --cnd) { // P is inverted inside the S^-1 storage: cap >= n
       PqpLayout probe;
-      if (fill_layout_tile(d, probe, per_cta, cnd, 2) == 0) {
+      if (fill_layout_tile(d, probe, per_cta, cnd, tctas, pis) == 0) {
         best = cnd;
         break;
       }
@@ -328,7 +332,7 @@ make_layout(pqp_batch* b)
     }
     const int need = d.ne + std::min(d.nc, std::max(8, (d.nc + 1) / 2));
     if (best >= std::min(d.cap, need)) {
-      fill_layout_tile(d, b->lay, per_cta, best, 2);
+      fill_layout_tile(d, b->lay, per_cta, best, tctas, pis);
       done = true;
     }
   }
