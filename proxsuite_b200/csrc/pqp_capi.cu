@@ -47,6 +47,7 @@ struct QpFlags
 } // namespace
 
 #define PQP_UPLOAD_CHUNKS 8
+#define PQP_CSTREAMS 4 // compute streams the chunks of a pipelined init + solve rotate over
 
 struct pqp_batch
 {
@@ -63,6 +64,14 @@ struct pqp_batch
   cudaStream_t copy_stream = nullptr; // host->device uploads of init(), chunked so that the set-up kernels overlap them
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   cudaEvent_t ev_main = nullptr, ev_chunk[PQP_UPLOAD_CHUNKS] = {};
+  cudaStream_t cstream[PQP_CSTREAMS] = {};
+  cudaEvent_t ev_cdone[PQP_CSTREAMS] = {};
+  // chunks of the last chunked init() whose set-up kernels are enqueued on cstream[k % PQP_CSTREAMS];
+  // a solve() that follows directly runs one launch per chunk on the same streams, so early
+  // chunks are solved while later ones are still crossing PCIe
+  int nchunks_pending = 0;
+  int64_t chunk_first[PQP_UPLOAD_CHUNKS] = {}, chunk_count[PQP_UPLOAD_CHUNKS] = {};
+  int64_t ws_slot_doubles = 0; // workspace stride between concurrently running chunk launches
   bool setup_timed = false, solve_timed = false;
   PqpLayout lay{};      // primary layout (fast kernel when the inverse blocks are in shared memory)
   PqpLayout lay_gen{};  // fallback: everything but the vectors in global memory, full capacity
@@ -319,6 +328,7 @@ make_layout(pqp_batch* b)
     const bool pis = tctas == 1;
     const int64_t per_cta = tctas == 1 ? (int64_t)max_smem : ((int64_t)smem_sm - 2 * 1024) / 2;
     int best = 0;
+    bool forced_tile_cap = false;
     for (int cnd = std::min(std::max(d.cap, d.n), 128); cnd >= std::max(d.n, d.ne + 1); --cnd) { // P is inverted inside the S^-1 storage: cap >= n
       PqpLayout probe;
       if (fill_layout_tile(d, probe, per_cta, cnd, tctas, pis) == 0) {
@@ -328,10 +338,13 @@ make_layout(pqp_batch* b)
     }
     if (const char* e = std::getenv("PQP_SI_CAP")) { // test hook: force a small capacity to exercise the retry path
       int v = std::atoi(e);
-      if (v >= std::max(d.n, d.ne + 1) && v < best) best = v;
+      if (v >= std::max(d.n, d.ne + 1) && v < best) {
+        best = v;
+        forced_tile_cap = true;
+      }
     }
     const int need = d.ne + std::min(d.nc, std::max(8, (d.nc + 1) / 2));
-    if (best >= std::min(d.cap, need)) {
+    if (best > 0 && (best >= std::min(d.cap, need) || forced_tile_cap)) {
       fill_layout_tile(d, b->lay, per_cta, best, tctas, pis);
       done = true;
     }
@@ -505,10 +518,11 @@ setup_results_and_flags(pqp_batch* b, int64_t i, char* need_zero = nullptr)
 }
 
 int
-launch_setup(pqp_batch* b, int64_t first, int64_t count, bool execute, bool reset_scaling, bool time_begin = true, bool time_end = true)
+launch_setup(pqp_batch* b, int64_t first, int64_t count, bool execute, bool reset_scaling, bool time_begin = true, bool time_end = true, cudaStream_t st = nullptr)
 {
+  if (!st) st = b->stream;
   // device needs the settings (preconditioner parameters) of these QPs
-  CUDA_TRY(cudaMemcpyAsync(b->p.params + first, b->hparams.data() + first, sizeof(PqpQpParams) * (size_t)count, cudaMemcpyHostToDevice, b->stream));
+  CUDA_TRY(cudaMemcpyAsync(b->p.params + first, b->hparams.data() + first, sizeof(PqpQpParams) * (size_t)count, cudaMemcpyHostToDevice, st));
   PqpSetupArgs a{};
   a.d = b->d;
   a.p = b->p;
@@ -516,12 +530,23 @@ launch_setup(pqp_batch* b, int64_t first, int64_t count, bool execute, bool rese
   a.count = (int32_t)count;
   a.execute = execute ? 1 : 0;
   a.reset_scaling = reset_scaling ? 1 : 0;
-  if (time_begin) CUDA_TRY(cudaEventRecord(b->ev0, b->stream));
-  int rc = pqp_launch_setup(&a, b->stream);
+  if (time_begin) CUDA_TRY(cudaEventRecord(b->ev0, st));
+  int rc = pqp_launch_setup(&a, st);
   if (rc != 0) return fail(PQP_ECUDA, std::string("setup kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
-  if (time_end) CUDA_TRY(cudaEventRecord(b->ev1, b->stream));
+  if (time_end) CUDA_TRY(cudaEventRecord(b->ev1, st));
   b->setup_timed = true;
   b->launches += 1;
+  return 0;
+}
+
+// later work on the main stream is ordered after everything enqueued on the chunk streams
+int
+join_cstreams(pqp_batch* b)
+{
+  for (int j = 0; j < PQP_CSTREAMS; ++j) {
+    CUDA_TRY(cudaEventRecord(b->ev_cdone[j], b->cstream[j]));
+    CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_cdone[j], 0));
+  }
   return 0;
 }
 
@@ -551,9 +576,11 @@ do_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const doubl
   // Host inputs of a large range are uploaded in chunks on a second stream; the set-up kernel of
   // chunk k runs while chunk k+1 is still crossing PCIe.
   const int nchunks = (!dev_ptrs && count >= 256) ? (int)std::min<int64_t>(PQP_UPLOAD_CHUNKS, count / 128) : 1;
+  b->nchunks_pending = 0;
   if (nchunks > 1) {
     CUDA_TRY(cudaEventRecord(b->ev_main, b->stream)); // uploads must not overtake kernels still reading the buffers
     CUDA_TRY(cudaStreamWaitEvent(b->copy_stream, b->ev_main, 0));
+    for (int j = 0; j < PQP_CSTREAMS; ++j) CUDA_TRY(cudaStreamWaitEvent(b->cstream[j], b->ev_main, 0));
   }
   for (int k = 0; k < nchunks; ++k) {
     const int64_t f = first + count * k / nchunks, e = first + count * (k + 1) / nchunks, cnt = e - f, o = f - first;
@@ -570,11 +597,20 @@ do_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const doubl
       if (int rc = copy_in(b, b->p.l_box, at(l_box, n), f, cnt, n, dev_ptrs, st)) return rc;
       if (int rc = copy_in(b, b->p.u_box, at(u_box, n), f, cnt, n, dev_ptrs, st)) return rc;
     }
+    cudaStream_t cs = b->stream;
     if (nchunks > 1) {
+      cs = b->cstream[k % PQP_CSTREAMS];
       CUDA_TRY(cudaEventRecord(b->ev_chunk[k], b->copy_stream));
-      CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_chunk[k], 0));
+      CUDA_TRY(cudaStreamWaitEvent(cs, b->ev_chunk[k], 0));
+      b->chunk_first[k] = f;
+      b->chunk_count[k] = cnt;
     }
-    if (int rc = launch_setup(b, f, cnt, compute_preconditioner != 0, compute_preconditioner == 0, k == 0, k == nchunks - 1)) return rc;
+    if (int rc = launch_setup(b, f, cnt, compute_preconditioner != 0, compute_preconditioner == 0, k == 0, k == nchunks - 1, cs)) return rc;
+  }
+  if (nchunks > 1) {
+    if (int rc = join_cstreams(b)) return rc;
+    // the whole batch, freshly initialised: a solve() issued next may run chunk by chunk
+    if (first == 0 && count == b->B && b->ws_slot_doubles > 0) b->nchunks_pending = nchunks;
   }
   return 0;
 }
@@ -587,27 +623,29 @@ fill_vec(std::vector<double>& v, double val)
 
 // upload the per-QP launch parameters and enqueue one persistent solve kernel
 int
-enqueue_solve(pqp_batch* b, cudaStream_t st, const PqpLayout& lay, int grid)
+enqueue_solve(pqp_batch* b, cudaStream_t st, const PqpLayout& lay, int grid, int64_t first = 0, int64_t count = -1, int slot = 0, bool timed = true)
 {
-  CUDA_TRY(cudaMemcpyAsync(b->p.params, b->hparams.data(), sizeof(PqpQpParams) * (size_t)b->B, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemsetAsync(b->counter, 0, sizeof(int32_t), st));
+  if (count < 0) count = b->B;
+  CUDA_TRY(cudaMemcpyAsync(b->p.params + first, b->hparams.data() + first, sizeof(PqpQpParams) * (size_t)count, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(b->counter + slot, 0, sizeof(int32_t), st));
   PqpSolveArgs a{};
   a.d = b->d;
   a.p = b->p;
   a.lay = lay;
-  a.batch = (int32_t)b->B;
-  a.counter = b->counter;
-  a.ws = b->ws;
+  a.batch = (int32_t)count;
+  a.first = (int32_t)first;
+  a.counter = b->counter + slot;
+  a.ws = b->ws + (size_t)slot * (size_t)b->ws_slot_doubles;
   a.dbg = b->dbg;
   a.dbg_cap = b->dbg_cap;
   a.dbg_qp = 0;
   a.prof = b->prof;
   if (const char* e = std::getenv("PQP_DEBUG_TRACE")) a.dbg_qp = std::atoi(e);
   if (const char* e = std::getenv("PQP_WATCHDOG_MS")) a.watchdog_ns = 1000000ull * (unsigned long long)std::atoll(e);
-  CUDA_TRY(cudaEventRecord(b->ev2, st));
+  if (timed) CUDA_TRY(cudaEventRecord(b->ev2, st));
   int rc = pqp_launch_solve(&a, grid, st);
   if (rc != 0) return fail(PQP_ECUDA, std::string("solve kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
-  CUDA_TRY(cudaEventRecord(b->ev3, st));
+  if (timed) CUDA_TRY(cudaEventRecord(b->ev3, st));
   return 0;
 }
 
@@ -752,7 +790,7 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
   rc |= dev_alloc(b, &p.si, B * nc);
   rc |= dev_alloc(b, &p.info, B * PQP_INFO_DOUBLES);
   rc |= dev_alloc(b, &p.params, B);
-  rc |= dev_alloc(b, &b->counter, 1);
+  rc |= dev_alloc(b, &b->counter, PQP_CSTREAMS + 1);
   if (rc != 0) {
     pqp_batch_destroy(b);
     return nullptr;
@@ -784,6 +822,8 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
   }
   bool aux_ok = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < PQP_UPLOAD_CHUNKS; ++k) aux_ok = aux_ok && cudaEventCreateWithFlags(&b->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < PQP_CSTREAMS; ++k)
+    aux_ok = aux_ok && cudaStreamCreateWithFlags(&b->cstream[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&b->ev_cdone[k], cudaEventDisableTiming) == cudaSuccess;
   if (!aux_ok || cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess || cudaEventCreate(&b->ev2) != cudaSuccess ||
       cudaEventCreate(&b->ev3) != cudaSuccess) {
     fail(PQP_ECUDA, "stream/event creation failed");
@@ -807,7 +847,14 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
     };
     b->grid = grid_for(b->lay);
     b->grid_gen = grid_for(b->lay_gen);
-    const size_t ws = std::max((size_t)b->grid * (size_t)b->lay.ws_doubles, (size_t)b->grid_gen * (size_t)b->lay_gen.ws_doubles);
+    size_t ws = std::max((size_t)b->grid * (size_t)b->lay.ws_doubles, (size_t)b->grid_gen * (size_t)b->lay_gen.ws_doubles);
+    // pipelined init + solve: up to PQP_CSTREAMS chunk launches run concurrently, each with its own workspace slice
+    const int64_t nch = batch >= 256 ? std::min<int64_t>(PQP_UPLOAD_CHUNKS, batch / 128) : 1;
+    if (nch > 1) {
+      const int64_t cmax = (batch + nch - 1) / nch;
+      b->ws_slot_doubles = std::min<int64_t>(b->grid, cmax) * b->lay.ws_doubles;
+      ws = std::max(ws, (size_t)PQP_CSTREAMS * (size_t)b->ws_slot_doubles);
+    }
     if (dev_alloc(b, &b->ws, ws) != 0) {
       pqp_batch_destroy(b);
       return nullptr;
@@ -836,6 +883,13 @@ pqp_batch_destroy(pqp_batch* b)
   if (b->ev_main) cudaEventDestroy(b->ev_main);
   for (int k = 0; k < PQP_UPLOAD_CHUNKS; ++k)
     if (b->ev_chunk[k]) cudaEventDestroy(b->ev_chunk[k]);
+  for (int k = 0; k < PQP_CSTREAMS; ++k) {
+    if (b->cstream[k]) {
+      cudaStreamSynchronize(b->cstream[k]);
+      cudaStreamDestroy(b->cstream[k]);
+    }
+    if (b->ev_cdone[k]) cudaEventDestroy(b->ev_cdone[k]);
+  }
   if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
@@ -900,6 +954,7 @@ pqp_batch_update(pqp_batch* b, int64_t first, int64_t count, const double* H, co
   if (!d.box && (l_box || u_box))
     return fail(PQP_EINVAL, "wrong model setup: the QP object is designed without box constraints, but the update includes lower or upper box inequalities.");
   CUDA_TRY(cudaSetDevice(b->device));
+  b->nchunks_pending = 0; // work enqueued on the main stream from here on: the next solve is a single launch
   // wrapper.hpp:743-746: update before init == init (per QP); handle the
   // common case where the whole range is in the same state.
   bool all_init = true, none_init = true;
@@ -948,6 +1003,7 @@ pqp_batch_warm_start(pqp_batch* b, int64_t first, int64_t count, const double* x
   if (int rc = check_range(b, first, count)) return rc;
   if (!x && !y && !z) return 0;
   CUDA_TRY(cudaSetDevice(b->device));
+  b->nchunks_pending = 0;
   for (int64_t i = first; i < first + count; ++i) b->hparams[i].s.initial_guess = PQP_WARM_START; // sticky, helpers.hpp:727
   if (int rc = copy_in(b, b->p.x, x, first, count, b->d.n, false)) return rc;
   if (int rc = copy_in(b, b->p.y, y, first, count, b->d.ne, false)) return rc;
@@ -999,7 +1055,23 @@ pqp_batch_solve_async(pqp_batch* b, void* stream_)
     p.mu_eq = info.mu_eq;
     p.mu_in = info.mu_in;
   }
-  if (int rc = enqueue_solve(b, st, b->lay, b->grid)) return rc;
+  bool all_active = true;
+  for (int64_t i = 0; i < b->B; ++i) all_active = all_active && b->hparams[i].active;
+  if (!stream_ && b->nchunks_pending > 1 && all_active && !b->prof && !b->dbg && !std::getenv("PQP_NO_PIPELINE")) {
+    // pipelined: one launch per uploaded chunk, on the stream that runs the chunk's set-up kernel
+    CUDA_TRY(cudaEventRecord(b->ev2, b->cstream[0])); // solve_ms then spans first chunk start .. last chunk end
+    for (int k = 0; k < b->nchunks_pending; ++k) {
+      const int64_t cnt = b->chunk_count[k];
+      const int grid = (int)std::min<int64_t>(b->grid, cnt);
+      if (int rc = enqueue_solve(b, b->cstream[k % PQP_CSTREAMS], b->lay, grid, b->chunk_first[k], cnt, k % PQP_CSTREAMS, false)) return rc;
+    }
+    if (int rc = join_cstreams(b)) return rc;
+    CUDA_TRY(cudaEventRecord(b->ev3, b->stream));
+    b->launches += b->nchunks_pending - 1;
+  } else if (int rc = enqueue_solve(b, st, b->lay, b->grid)) {
+    return rc;
+  }
+  b->nchunks_pending = 0;
   b->solve_timed = true;
   b->launches += 1;
   b->solve_pending = true;
@@ -1153,6 +1225,7 @@ pqp_batch_cleanup(pqp_batch* b, int64_t first, int64_t count)
 {
   if (int rc = check_range(b, first, count)) return rc;
   CUDA_TRY(cudaSetDevice(b->device));
+  b->nchunks_pending = 0;
   if (int rc = zero_results(b, first, count)) return rc;
   for (int64_t i = first; i < first + count; ++i) {
     cold_start(b->hinfo[i], &b->hparams[i].s, b->backend);

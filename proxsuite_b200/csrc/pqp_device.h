@@ -112,7 +112,8 @@ struct PqpSolveArgs
   PqpDims d;
   PqpBatchPtrs p;
   PqpLayout lay;
-  int32_t batch;
+  int32_t batch;     // number of QPs this launch owns
+  int32_t first;     // first QP of this launch
   int32_t* counter;  // dynamic work queue (replaces OpenMP schedule(dynamic), qp_solve.hpp:55)
   double* ws;        // per-CTA workspace base
   double* dbg;       // optional debug trace buffer (NULL = off)

@@ -2098,9 +2098,9 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArg
   while (true) {
     if (threadIdx.x == 0) cur_q = atomicAdd(A.counter, 1);
     __syncthreads();
-    const int q = cur_q;
+    const int q = A.first + cur_q; // this launch owns the QPs [first, first + batch)
     __syncthreads();
-    if (q >= A.batch) break;
+    if (cur_q >= A.batch) break;
     if (!A.p.params[q].active) continue;
     if (threadIdx.x == 0) c.As = As_home;
     __syncthreads();

@@ -328,3 +328,63 @@ def test_compact_layout_overflow_retry(px, oracle, monkeypatch):
     for i in range(B):
         pri, dua = kkt_residuals(data[i], r_small["x"][i], r_small["y"][i], r_small["z"][i])
         assert pri <= EPS and dua <= EPS
+
+
+def test_tile_layout_overflow_retry(px, oracle, monkeypatch):
+    """Tile kernel with a deliberately small S^-1 capacity: QPs whose active set
+    outgrows it report the internal code and are re-solved by the general kernel."""
+    B, n, ne, ni = 32, 20, 6, 40
+    data = [px.dense.random_qp("strongly_convex", i, n, ne, ni) for i in range(B)]
+    st = {k: np.stack([d[k] for d in data]) for k in KEYS}
+
+    def run():
+        db = px.dense.DenseBatch(B, n, ne, ni)
+        db.settings.eps_abs = EPS
+        db.settings.eps_rel = 0
+        db.settings.initial_guess = px.InitialGuess.NO_INITIAL_GUESS
+        db.init(**st)
+        db.solve()
+        return db.results(), db.launch_config()
+
+    r_ref, _ = run()
+    monkeypatch.setenv("PQP_LAYOUT", "tile")
+    monkeypatch.setenv("PQP_SI_CAP", str(ne + 16))
+    r_small, cfg_small = run()
+    assert cfg_small["si_cap"] == ne + 16
+    assert cfg_small["overflow_retries"] > 0, "the test shape must overflow the forced capacity"
+    assert (r_small["info"]["status"] == 0).all() and (r_ref["info"]["status"] == 0).all()
+    assert np.abs(r_small["x"] - r_ref["x"]).max() <= 1e-7
+    for i in range(B):
+        pri, dua = kkt_residuals(data[i], r_small["x"][i], r_small["y"][i], r_small["z"][i])
+        assert pri <= EPS and dua <= EPS
+
+
+def test_pipelined_init_solve_equals_single_launch(px, monkeypatch):
+    """A large init() uploads in chunks and a solve() issued right after runs one
+    launch per chunk while later chunks are still being copied; the results must
+    be bit-identical to the single persistent launch, and a re-init must not see
+    stale chunk state."""
+    B, n, ne, ni = 384, 30, 10, 30
+    data = [px.dense.random_qp("strongly_convex", i, n, ne, ni) for i in range(B)]
+    st = {k: np.stack([d[k] for d in data]) for k in KEYS}
+
+    def run(db=None):
+        if db is None:
+            db = px.dense.DenseBatch(B, n, ne, ni)
+            db.settings.eps_abs = EPS
+            db.settings.eps_rel = 0
+            db.settings.initial_guess = px.InitialGuess.NO_INITIAL_GUESS
+        db.init(**st)
+        db.solve()
+        return db, db.results()
+
+    db, r_pipe = run()
+    launches_pipe = db.timings()["kernel_launches"]
+    _, r_pipe2 = run(db)  # same batch object again
+    monkeypatch.setenv("PQP_NO_PIPELINE", "1")
+    db1, r_one = run()
+    assert launches_pipe > db1.timings()["kernel_launches"], "the first run must have used per-chunk launches"
+    assert (r_one["info"]["status"] == 0).all()
+    for k in ("x", "y", "z"):
+        assert np.array_equal(r_pipe[k], r_one[k]) and np.array_equal(r_pipe2[k], r_one[k])
+    assert np.array_equal(r_pipe["info"]["iter"], r_one["info"]["iter"])
