@@ -243,7 +243,7 @@ fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_ca
   vsz[V_DX] = n; vsz[V_DS] = sc; vsz[V_DZ] = nc;
   vsz[V_RX] = n; vsz[V_RS] = sc; vsz[V_EX] = n; vsz[V_ES] = sc;
   vsz[V_DUAL] = n; vsz[V_SE] = ne + nc + 2; vsz[V_RUP] = 0; vsz[V_SI] = nc; // [A x; C x] contiguous
-  vsz[V_HDX] = n; vsz[V_ADX] = ne + nc + 2; vsz[V_ATDY] = n; vsz[V_CDX] = 0; vsz[V_CTDZ] = 2; vsz[V_Q] = n; // [A dx; C dx] contiguous
+  vsz[V_HDX] = n; vsz[V_ADX] = ne + nc + 2; vsz[V_ATDY] = n; vsz[V_CDX] = 0; vsz[V_CTDZ] = n; vsz[V_Q] = n; // [A dx; C dx] contiguous
   vsz[V_GS] = n; vsz[V_BS] = ne; vsz[V_US] = nc; vsz[V_LS] = nc; vsz[V_IS] = 2; vsz[V_DELTA] = n + ne + nc;
   vsz[V_B] = ne; vsz[V_U] = nc; vsz[V_L] = nc;
   vsz[V_D1INV] = 2; vsz[V_DSV] = 2; vsz[V_DSINV] = 2;

@@ -38,6 +38,7 @@ struct Ctx
   int pi_smem;     // 1: P^-1 lives in shared memory (else global, read through L2)
   int si_cap;      // largest dual-block size the S^-1 storage can hold
   int uv_ld;       // leading dimension of the 8 sweep panel vectors kept in `scratch`
+  int si_valid;    // 0: the dual block has not been formed yet (deferred to the first active-set change)
   int overflow;    // set when an insertion would exceed si_cap (QP is retried by the generic kernel)
 };
 
@@ -242,7 +243,7 @@ __device__ __forceinline__ void reduce_rows(double (&d)[RR], int lane)
 // using the symmetry of H_s and P^-1. Rows must be 16-byte aligned (ld even).
 // ---------------------------------------------------------------------------
 template<int NCH>
-__device__ void axpy_pass_t(const Ctx& c, const double* __restrict__ base0, int split, const double* __restrict__ base1, int ld, const int* __restrict__ list, int byid, int nrows, const double* __restrict__ coef, int ncols, double* out, const double* add, double sign)
+__device__ void axpy_pass_t(const Ctx& c, const double* __restrict__ base0, int split, const double* __restrict__ base1, int ld, const int* __restrict__ list, int byid, int nrows, const double* __restrict__ coef, int ncols, double* out, const double* add, double sign, double* raw)
 {
   constexpr int UNR = (NCH <= 2) ? 8 : 4; // rows in flight per warp (L2 latency is the bound)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -311,21 +312,22 @@ __device__ void axpy_pass_t(const Ctx& c, const double* __restrict__ base0, int 
 #pragma unroll
     for (int w = 0; w < NW; ++w) s += scr[w * 2 * np + j];
     out[j] = (add ? add[j] : 0.0) + sign * s;
+    if (raw) raw[j] = s; // the plain sum, for callers that need both
   }
   __syncthreads();
 }
 
-__device__ __noinline__ void axpy_pass2(const Ctx& c, const double* base0, int split, const double* base1, int ld, const int* list, int byid, int nrows, const double* coef, int ncols, double* out, const double* add, double sign)
+__device__ __noinline__ void axpy_pass2(const Ctx& c, const double* base0, int split, const double* base1, int ld, const int* list, int byid, int nrows, const double* coef, int ncols, double* out, const double* add, double sign, double* raw = nullptr)
 {
   const int np = (ncols + 1) >> 1;
   if (np <= 32)
-    axpy_pass_t<1>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign);
+    axpy_pass_t<1>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign, raw);
   else if (np <= 64)
-    axpy_pass_t<2>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign);
+    axpy_pass_t<2>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign, raw);
   else if (np <= 96)
-    axpy_pass_t<3>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign);
+    axpy_pass_t<3>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign, raw);
   else
-    axpy_pass_t<4>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign);
+    axpy_pass_t<4>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign, raw);
 }
 // all rows from one matrix
 __device__ __forceinline__ void axpy_pass(const Ctx& c, const double* base, int ld, int nrows, const double* coef, int ncols, double* out, const double* add, double sign)
@@ -739,7 +741,10 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
   const int ns = c.ns, n = c.n, ne = c.ne;
   if (ns == 0) {
     apply_Pinv(c, b1, v_t1);
-    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) ox[j] = v_t1[j];
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
+      ox[j] = v_t1[j];
+      v_ctdz[j] = 0.0;
+    }
     __syncthreads();
     return;
   }
@@ -749,8 +754,9 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
   _Pragma("unroll 1") for (int s = threadIdx.x; s < ns; s += NT) v_s1[s] = c.kt[row_id(c, s)] - b2[s];
   __syncthreads();
   tsym_mv(c, c.Si, v_s1, os, ns);
-  // t2 = b1 - B^T lam : equality rows, then the active rows of C_s
-  axpy_pass2(c, c.As, ne, c.Cs, n, c.slot_cons, 0, ns, os, n, v_t2, b1, -1.0);
+  // t2 = b1 - B^T lam : equality rows, then the active rows of C_s. B^T lam itself is kept
+  // (v_ctdz): kkt_residual needs exactly this product for the residual of the x block.
+  axpy_pass2(c, c.As, ne, c.Cs, n, c.slot_cons, 0, ns, os, n, v_t2, b1, -1.0, v_ctdz);
   apply_Pinv(c, v_t2, ox);
 }
 
@@ -872,6 +878,8 @@ __device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_i
   }
   __syncthreads();
   tsym_sweep_invert(c, c.Si, v_scratch, c.uv_ld, ns);
+  if (threadIdx.x == 0) c.si_valid = 1;
+  __syncthreads();
 }
 
 // P^-1 = (Hs + rho I)^-1, explicit: swept in the (free) S^-1 tile storage, then
@@ -961,16 +969,19 @@ struct Scal
 
 // err = rhs - K dw, with the by-products the Newton loop reuses
 // (solver.hpp:245-318; quirk 3 of SURVEY Appendix A). Returns |err|_inf.
-__device__ __noinline__ double kkt_residual(const Ctx& c, const Scal& sc)
+__device__ __noinline__ double kkt_residual(const Ctx& c, const Scal& sc, bool first)
 {
   PQP_VECS(c);
   const int n = c.n, ne = c.ne, ns = c.ns;
   axpy_pass(c, c.Hs, n, n, v_dx, n, v_hdx, nullptr, 1.0);                    // H dx (H symmetric)
   axpy_pass(c, c.Bt, c.ldb, n, v_dx, ne + c.ni, v_adx, nullptr, 1.0);        // [A dx; C dx] (adx, cdx contiguous)
-  axpy_pass2(c, c.As, ne, c.Cs, n, c.slot_cons, 0, ns, v_ds, n, v_atdy, nullptr, 1.0); // A^T dy + C_J^T dz_J
+  // A^T dy + C_J^T dz_J is B^T lam of the solve that produced (dx, ds) (first call) or of the
+  // refinement step just added to it: no third pass over the constraint rows
   double m = 0;
   _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
-    double e = v_rx[j] - (v_hdx[j] + sc.rho * v_dx[j] + v_atdy[j]); // atdy = A^T dy + C_J^T dz_J
+    const double at = first ? v_ctdz[j] : v_atdy[j] + v_ctdz[j];
+    v_atdy[j] = at;
+    double e = v_rx[j] - (v_hdx[j] + sc.rho * v_dx[j] + at); // atdy = A^T dy + C_J^T dz_J
     v_ex[j] = e;
     m = nanmax(m, fabs(e));
   }
@@ -1008,7 +1019,7 @@ __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_setting
     solve_kkt(c, v_rx, v_rs, v_dx, v_ds);
     PROF_ADD(PH_SOLVE, tp);
     tp = PROF_T0();
-    double err = kkt_residual(c, sc);
+    double err = kkt_residual(c, sc, true);
     PROF_ADD(PH_RESID, tp);
     ++it;
     double prev = err;
@@ -1022,7 +1033,7 @@ __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_setting
       __syncthreads();
       PROF_ADD(PH_SOLVE, tp);
       tp = PROF_T0();
-      err = kkt_residual(c, sc);
+      err = kkt_residual(c, sc, false);
       PROF_ADD(PH_RESID, tp);
       if (err > prev)
         it_stab += 1;
@@ -1059,7 +1070,7 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
   // A bordering step costs two passes over S^-1; a rebuild from G costs (ns+nadd)/4 block
   // sweeps of the same size. Many simultaneous additions (the first Newton steps) are
   // therefore registered at once and S^-1 is re-formed from the Gram matrix.
-  if (nadd >= 8 && 2 * nadd >= (c.ns + nadd + 3) / 4) {
+  if (!c.si_valid || (nadd >= 8 && 2 * nadd >= (c.ns + nadd + 3) / 4)) {
     if (c.ns + nadd > c.si_cap) {
       if (threadIdx.x == 0) c.overflow = 1;
       __syncthreads();
@@ -1520,7 +1531,17 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
   build_G(c);
   PROF_ADD(PH_EQ, tph);
   tph = PROF_T0();
-  build_dual_block(c, ne, sc.mu_eq, sc.mu_in);
+  if (prm.start_mode == PQP_START_EQ_GUESS) {
+    build_dual_block(c, ne, sc.mu_eq, sc.mu_in);
+  } else {
+    // the equality block alone is never used: the first active-set change forms S^-1 for
+    // equalities + active inequalities in one inversion
+    if (tid == 0) {
+      c.ns = ne;
+      c.si_valid = 0;
+    }
+    __syncthreads();
+  }
   PROF_ADD(PH_EQ, tph);
 
   if (prm.start_mode == PQP_START_EQ_GUESS) {
