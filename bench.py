@@ -115,6 +115,15 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """Every host thread this process may use. torchrun exports OMP_NUM_THREADS=1 to its
+    workers; the CPU arm must not inherit that, so the count is passed explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(sample, reps, threads=0):
     """The oracle (C++ restatement of the reference, kind "port") on the host
     cores: OpenMP schedule(dynamic) over QPs with all threads, batch already
@@ -122,7 +131,7 @@ def cpu_baseline(sample, reps, threads=0):
     from oracle import oracle as O
 
     O.build()
-    T = threads or O.omp_max_threads()
+    T = threads or host_threads()
     st = generate(0, sample, O.generate_qp)
     b = O.OracleBatch(sample, N_DIM, N_EQ, N_IN)
     for i in range(sample):
@@ -149,11 +158,11 @@ def run_reference(args, rank, world):
     port with every host thread; rank 0 alone runs."""
     if rank != 0:
         return
-    sample = 256
+    sample = 1024  # the whole per-GPU batch of the GPU arm
     from oracle import oracle as O
 
     O.build()
-    T = O.omp_max_threads()
+    T = host_threads()
     st = generate(0, sample, O.generate_qp)
     b = O.OracleBatch(sample, N_DIM, N_EQ, N_IN)
     for i in range(sample):
