@@ -175,6 +175,7 @@ fill_layout(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, bool want_m1, 
   vsz[V_SCRATCH] = std::max<int>(vsz[V_SCRATCH], 8 * ((std::max(n, cap) + 2) & ~1)); // 8 panel vectors of the blocked sweep
   vsz[V_RED] = PQP_NW * 16; // block_reduce: up to 10 values per warp
   vsz[V_KT] = 2;
+  vsz[V_KT2] = 2;
   int off = 0;
   for (int v = 0; v < V_COUNT; ++v) {
     L.voff[v] = off;
@@ -253,7 +254,8 @@ fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_ca
   const int uv_ld = (std::max(n, si_cap) + 2) & ~1;
   vsz[V_SCRATCH] = std::max(std::max(8 * uv_ld, PQP_NW * 128), PQP_NW * (std::max(n, ne + d.ni) + 2));
   vsz[V_RED] = PQP_NW * 16;
-  vsz[V_KT] = ne + d.ni + 2;
+  vsz[V_KT] = ne + d.ni + 4;
+  vsz[V_KT2] = ne + d.ni + 4;
   int off = 0;
   for (int v = 0; v < V_COUNT; ++v) {
     L.voff[v] = off;

@@ -89,6 +89,7 @@ enum PqpVec {
   V_SCRATCH,                 // partial-sum scratch
   V_RED,                     // reduction scratch (64)
   V_KT,                      // ne + ni products of one Bt pass (tile layout)
+  V_KT2,                     // second dense coefficient vector (tile layout)
   V_COUNT
 };
 

@@ -13,7 +13,8 @@ struct Ctx
   // factor storage
   double *Pi, *As, *Si, *G, *Y;
   double* Bt;      // [A_s; C_s]^T, n x ldb (L2 workspace)
-  double* kt;      // ne + ni products of one Bt pass (shared memory)
+  double* kt;      // ne + ni products of one Bt pass / dense coefficient vector of a B^T product (shared memory)
+  double* kt2;     // second dense coefficient vector (global dual residual)
   double* W;       // P^-1 B^T, n x ldb (L2 workspace; only needed to form G)
   int ldb, ldn;    // leading dimensions of Bt and Pi (even)
   const double *Hs, *Cs;        // scaled matrices of this QP (global)
@@ -333,6 +334,87 @@ __device__ __noinline__ void axpy_pass2(const Ctx& c, const double* base0, int s
 __device__ __forceinline__ void axpy_pass(const Ctx& c, const double* base, int ld, int nrows, const double* coef, int ncols, double* out, const double* add, double sign)
 {
   axpy_pass2(c, base, nrows, base, ld, nullptr, 0, nrows, coef, ncols, out, add, sign);
+}
+
+// Products with B^T through the SAME transposed copy Bt (row j of Bt = column j of B = [A_s; C_s]):
+//   out1[j] = add[j] + sign * (Bt[j,:] . coef1),  raw1[j] = the plain dot,  out2[j] = Bt[j,:] . coef2
+// coef vectors are dense over the ne + ni constraint rows (zero where a row does not take part).
+// A warp owns four rows at a time; the four row sums share one transpose-reduction. Using Bt for
+// both B v (AXPY form) and B^T lam (this form) keeps A_s / C_s out of the L2 working set of the
+// iteration (they are read once, to build Bt).
+template<int NCH, bool TWO>
+__device__ void bt_dot_t(const Ctx& c, const double* __restrict__ coef1, const double* __restrict__ coef2, double* out1, const double* add, double sign, double* raw1, double* out2)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = c.n, np = c.ldb >> 1;
+  PQP_SM(coef1);
+  PQP_SM(out1);
+  if (TWO) {
+    PQP_SM(coef2);
+    PQP_SM(out2);
+  }
+  bool pv[NCH];
+  double2 c1[NCH], c2[NCH];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    pv[ch] = lane + 32 * ch < np;
+    c1[ch] = pv[ch] ? reinterpret_cast<const double2*>(coef1)[lane + 32 * ch] : make_double2(0.0, 0.0);
+    c2[ch] = (TWO && pv[ch]) ? reinterpret_cast<const double2*>(coef2)[lane + 32 * ch] : make_double2(0.0, 0.0);
+  }
+  _Pragma("unroll 1") for (int jb = warp; jb < n; jb += 4 * NW) {
+    double2 v[4][NCH];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = jb + u * NW;
+      const double2* rp = reinterpret_cast<const double2*>(c.Bt + (size_t)(j < n ? j : 0) * c.ldb) + lane;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) v[u][ch] = (j < n && pv[ch]) ? rp[32 * ch] : make_double2(0.0, 0.0);
+    }
+    double d1[4], d2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        a1 = fma(v[u][ch].x, c1[ch].x, a1);
+        a1 = fma(v[u][ch].y, c1[ch].y, a1);
+        if (TWO) {
+          a2 = fma(v[u][ch].x, c2[ch].x, a2);
+          a2 = fma(v[u][ch].y, c2[ch].y, a2);
+        }
+      }
+      d1[u] = a1;
+      d2[u] = a2;
+    }
+    reduce_rows<4>(d1, lane);
+    if (TWO) reduce_rows<4>(d2, lane);
+    if ((lane & 7) == 0) {
+      const int j = jb + (lane >> 3) * NW;
+      if (j < n) {
+        out1[j] = (add ? add[j] : 0.0) + sign * d1[0];
+        if (raw1) raw1[j] = d1[0];
+        if (TWO) out2[j] = d2[0];
+      }
+    }
+  }
+  __syncthreads();
+}
+__device__ __noinline__ void bt_dot(const Ctx& c, const double* coef1, const double* coef2, double* out1, const double* add, double sign, double* raw1, double* out2)
+{
+  const int np = c.ldb >> 1;
+  if (coef2) {
+    if (np <= 64)
+      bt_dot_t<2, true>(c, coef1, coef2, out1, add, sign, raw1, out2);
+    else
+      bt_dot_t<4, true>(c, coef1, coef2, out1, add, sign, raw1, out2);
+  } else {
+    if (np <= 64)
+      bt_dot_t<2, false>(c, coef1, coef2, out1, add, sign, raw1, out2);
+    else if (np <= 96)
+      bt_dot_t<3, false>(c, coef1, coef2, out1, add, sign, raw1, out2);
+    else
+      bt_dot_t<4, false>(c, coef1, coef2, out1, add, sign, raw1, out2);
+  }
 }
 
 // Out[i][c] = sum_{k < K} CM[k][i] * R[k][c]   (Out = CM^T R), i < M, c < ncols,
@@ -754,9 +836,20 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
   _Pragma("unroll 1") for (int s = threadIdx.x; s < ns; s += NT) v_s1[s] = c.kt[row_id(c, s)] - b2[s];
   __syncthreads();
   tsym_mv(c, c.Si, v_s1, os, ns);
-  // t2 = b1 - B^T lam : equality rows, then the active rows of C_s. B^T lam itself is kept
-  // (v_ctdz): kkt_residual needs exactly this product for the residual of the x block.
-  axpy_pass2(c, c.As, ne, c.Cs, n, c.slot_cons, 0, ns, os, n, v_t2, b1, -1.0, v_ctdz);
+  // lam scattered to constraint order (zero on inactive rows), then t2 = b1 - B^T lam.
+  // B^T lam itself is kept (v_ctdz): kkt_residual needs exactly this product for the x block.
+  _Pragma("unroll 1") for (int id = threadIdx.x; id < c.ldb; id += NT) {
+    double lam = 0.0;
+    if (id < ne) {
+      lam = os[id];
+    } else if (id < ne + c.ni) {
+      const int s = c.cons_slot[id - ne];
+      if (s >= 0) lam = os[s];
+    }
+    c.kt[id] = lam;
+  }
+  __syncthreads();
+  bt_dot(c, c.kt, nullptr, v_t2, b1, -1.0, v_ctdz, nullptr);
   apply_Pinv(c, v_t2, ox);
 }
 
@@ -1116,8 +1209,13 @@ __device__ __noinline__ void global_passes(Ctx& c, bool primal, bool dual)
   const int n = c.n, ne = c.ne, ni = c.ni;
   if (dual) {
     axpy_pass(c, c.Hs, n, n, v_x, n, v_t1, nullptr, 1.0);
-    axpy_pass(c, c.As, n, ne, v_y, n, v_t2, nullptr, 1.0);
-    axpy_pass(c, c.Cs, n, ni, v_z, n, v_t3, nullptr, 1.0);
+    // A^T y and C^T z from one pass over Bt: coefficient vectors [y; 0] and [0; z]
+    _Pragma("unroll 1") for (int id = threadIdx.x; id < c.ldb; id += NT) {
+      c.kt[id] = (id < ne) ? v_y[id] : 0.0;
+      c.kt2[id] = (id >= ne && id < ne + ni) ? v_z[id - ne] : 0.0;
+    }
+    __syncthreads();
+    bt_dot(c, c.kt, c.kt2, v_t2, nullptr, 1.0, nullptr, v_t3);
   }
   if (primal) axpy_pass(c, c.Bt, c.ldb, n, v_x, ne + ni, v_se, nullptr, 1.0); // [A x; C x] (se, rup contiguous)
 }
@@ -1671,9 +1769,16 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
           break;
         }
         // q = sum over inactive constraints with z_i != 0 of z_i c_i
-        int nq = block_compact(c, nc, c.list2, [&](int i) { return c.cons_slot[i] < 0 && v_z[i] != 0.0; });
+        int nq = 0;
+        _Pragma("unroll 1") for (int id = tid; id < c.ldb; id += NT) {
+          double zq = 0.0;
+          if (id >= ne && id < ne + ni && c.cons_slot[id - ne] < 0) zq = v_z[id - ne];
+          c.kt[id] = zq;
+          nq |= (zq != 0.0) ? 1 : 0;
+        }
+        nq = __syncthreads_or(nq);
         if (nq > 0) {
-          axpy_pass2(c, c.Cs, 0, c.Cs, n, c.list2, 1, nq, v_z, n, v_q, nullptr, 1.0);
+          bt_dot(c, c.kt, nullptr, v_q, nullptr, 1.0, nullptr, nullptr);
         } else {
           _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_q[j] = 0;
         }
@@ -2054,6 +2159,7 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArg
     c.scratch = v + L.voff[V_SCRATCH];
     c.red = v + L.voff[V_RED];
     c.kt = v + L.voff[V_KT];
+    c.kt2 = v + L.voff[V_KT2];
     int* ib = reinterpret_cast<int*>(smem_dyn + L.smem_doubles);
     c.cons_slot = ib;
     c.slot_cons = c.cons_slot + A.d.nc;
