@@ -75,7 +75,8 @@ struct pqp_batch
   bool setup_timed = false, solve_timed = false;
   PqpLayout lay{};      // primary layout (fast kernel when the inverse blocks are in shared memory)
   PqpLayout lay_gen{};  // fallback: everything but the vectors in global memory, full capacity
-  int grid = 0, grid_gen = 0;
+  PqpLayout lay_big{};  // tile layout with the largest S^-1 capacity one CTA per SM allows (first retry level); kind 0 = unused
+  int grid = 0, grid_gen = 0, grid_big = 0;
   int32_t* counter = nullptr;
   double* ws = nullptr;
   double* dbg = nullptr;
@@ -349,6 +350,15 @@ make_layout(pqp_batch* b)
     if (best > 0 && (best >= std::min(d.cap, need) || forced_tile_cap)) {
       fill_layout_tile(d, b->lay, per_cta, best, tctas, pis);
       done = true;
+      // first retry level for QPs whose active set outgrows `best`: same kernel, one CTA per SM
+      std::memset(&b->lay_big, 0, sizeof(b->lay_big));
+      for (int cnd = std::min(std::max(d.cap, d.n), 128); cnd > best; --cnd) {
+        PqpLayout probe;
+        if (fill_layout_tile(d, probe, (int64_t)max_smem, cnd, 1, false) == 0) {
+          b->lay_big = probe;
+          break;
+        }
+      }
     }
   }
   if (!done && (m == "auto" || m == "compact")) {
@@ -850,6 +860,10 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
     b->grid = grid_for(b->lay);
     b->grid_gen = grid_for(b->lay_gen);
     size_t ws = std::max((size_t)b->grid * (size_t)b->lay.ws_doubles, (size_t)b->grid_gen * (size_t)b->lay_gen.ws_doubles);
+    if (b->lay_big.kind == 1) {
+      b->grid_big = grid_for(b->lay_big);
+      ws = std::max(ws, (size_t)b->grid_big * (size_t)b->lay_big.ws_doubles);
+    }
     // pipelined init + solve: up to PQP_CSTREAMS chunk launches run concurrently, each with its own workspace slice
     const int64_t nch = batch >= 256 ? std::min<int64_t>(PQP_UPLOAD_CHUNKS, batch / 128) : 1;
     if (nch > 1) {
@@ -1104,20 +1118,26 @@ pqp_batch_sync(pqp_batch* b)
       for (int64_t i = 0; i < b->B; ++i) {
         if (b->hparams[i].active && raw[(size_t)i * PQP_INFO_DOUBLES + 10] == 99.0) retry.push_back(i);
       }
-      if (!retry.empty()) {
+      if (!retry.empty()) b->overflow_retries += (int64_t)retry.size();
+      // level 1: the tile kernel with its largest capacity (one CTA per SM); level 2: the general kernel
+      for (int level = (b->lay_big.kind == 1 ? 1 : 2); level <= 2 && !retry.empty(); ++level) {
         std::vector<int32_t> saved((size_t)b->B);
         for (int64_t i = 0; i < b->B; ++i) {
           saved[i] = b->hparams[i].active;
           b->hparams[i].active = 0;
         }
         for (int64_t i : retry) b->hparams[i].active = 1;
-        int rc = enqueue_solve(b, b->stream, b->lay_gen, b->grid_gen);
+        int rc = (level == 1) ? enqueue_solve(b, b->stream, b->lay_big, b->grid_big) : enqueue_solve(b, b->stream, b->lay_gen, b->grid_gen);
         for (int64_t i = 0; i < b->B; ++i) b->hparams[i].active = saved[i];
         if (rc != 0) return rc;
         b->launches += 1;
-        b->overflow_retries += (int64_t)retry.size();
         CUDA_TRY(cudaStreamSynchronize(b->stream));
         CUDA_TRY(cudaMemcpy(raw.data(), b->p.info, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost));
+        std::vector<int64_t> still;
+        for (int64_t i : retry) {
+          if (raw[(size_t)i * PQP_INFO_DOUBLES + 10] == 99.0) still.push_back(i);
+        }
+        retry.swap(still);
       }
     }
     float ms_solve = 0, ms_setup = 0;
