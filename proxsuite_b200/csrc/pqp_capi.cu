@@ -246,17 +246,17 @@ fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_ca
   vsz[V_RX] = n; vsz[V_RS] = sc; vsz[V_EX] = n; vsz[V_ES] = sc;
   vsz[V_DUAL] = n; vsz[V_SE] = ne + nc + 2; vsz[V_RUP] = 0; vsz[V_SI] = nc; // [A x; C x] contiguous
   vsz[V_HDX] = n; vsz[V_ADX] = ne + nc + 2; vsz[V_ATDY] = n; vsz[V_CDX] = 0; vsz[V_CTDZ] = n; vsz[V_Q] = n; // [A dx; C dx] contiguous
-  vsz[V_GS] = n; vsz[V_BS] = ne; vsz[V_US] = nc; vsz[V_LS] = nc; vsz[V_IS] = 2; vsz[V_DELTA] = n + ne + nc;
+  vsz[V_GS] = n; vsz[V_BS] = ne; vsz[V_US] = nc; vsz[V_LS] = nc; vsz[V_IS] = d.box ? n : 2; vsz[V_DELTA] = n + ne + nc;
   vsz[V_B] = ne; vsz[V_U] = nc; vsz[V_L] = nc;
   vsz[V_D1INV] = 2; vsz[V_DSV] = 2; vsz[V_DSINV] = 2;
   vsz[V_T1] = n; vsz[V_T2] = n; vsz[V_T3] = n;
   vsz[V_S1] = sc; vsz[V_S2] = sc; vsz[V_S3] = sc; vsz[V_S4] = sc;
   vsz[V_ALPHAS] = 2 * nc + 2; vsz[V_GRADS] = 4;
   const int uv_ld = (std::max(n, si_cap) + 2) & ~1;
-  vsz[V_SCRATCH] = std::max(std::max(8 * uv_ld, PQP_NW * 128), PQP_NW * (std::max(n, ne + d.ni) + 2));
+  vsz[V_SCRATCH] = std::max(std::max(8 * uv_ld, PQP_NW * 128), PQP_NW * (std::max(n, ne + nc) + 2));
   vsz[V_RED] = PQP_NW * 16;
-  vsz[V_KT] = ne + d.ni + 4;
-  vsz[V_KT2] = ne + d.ni + 4;
+  vsz[V_KT] = ne + nc + 4;
+  vsz[V_KT2] = ne + nc + 4;
   int off = 0;
   for (int v = 0; v < V_COUNT; ++v) {
     L.voff[v] = off;
@@ -269,12 +269,12 @@ fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_ca
   L.si_cap = si_cap;
   L.ctas_per_sm = ctas;
   L.kind = 1;
-  const int ldn = (n + 1) & ~1, ldb = (ne + d.ni + 1) & ~1;
+  const int ldn = (n + 1) & ~1, ldb = (ne + nc + 1) & ~1;
   int64_t sz[PA_COUNT];
   sz[PA_M1] = rnd((int64_t)n * ldn + 4);
   sz[PA_AS] = rnd((int64_t)n * ldb + 4);              // Bt
   sz[PA_MS] = rnd(tile_doubles(si_cap));
-  sz[PA_G] = rnd((int64_t)(ne + d.ni) * ldb + 4);     // G, full square
+  sz[PA_G] = rnd((int64_t)(ne + nc) * ldb + 4);       // G, full square
   sz[PA_Y] = rnd((int64_t)n * ldb + 4);               // W
   sz[PA_VEC] = L.vec_doubles;
   const int64_t nlist = std::max(nc, cap);
@@ -323,8 +323,8 @@ make_layout(pqp_batch* b)
   // generic fallback first (always valid as long as the vectors fit somewhere)
   fill_layout(d, b->lay_gen, max_smem, false, false, false, d.cap, 1);
   bool done = false;
-  // tile layout (specialised kernel): dense Hessian, no box constraints, n even and <= 128
-  if ((m == "auto" || m == "tile") && d.hess == PQP_HESSIAN_DENSE && !d.box && (d.n % 2) == 0 && d.n <= 128 && d.n >= 2 && d.ne + d.ni <= 254 && d.nc > 0) {
+  // tile layout (specialised kernel): dense Hessian, n even and <= 128, at most 254 constraint rows
+  if ((m == "auto" || m == "tile") && d.hess == PQP_HESSIAN_DENSE && (d.n % 2) == 0 && d.n <= 128 && d.n >= 2 && d.ne + d.nc <= 254 && d.nc > 0) {
     // experiment hook: PQP_TILE_CTAS=1 -> one CTA per SM with P^-1 in shared memory as well
     const char* tce = std::getenv("PQP_TILE_CTAS");
     const int tctas = (tce && std::atoi(tce) == 1) ? 1 : 2;
@@ -346,6 +346,8 @@ make_layout(pqp_batch* b)
         forced_tile_cap = true;
       }
     }
+    // worth it only if the shared-memory S^-1 holds the equalities plus half of the inequality rows
+    // (cfg 3, box constraints: ~all QPs exceed 128 slots and would go through the retry levels)
     const int need = d.ne + std::min(d.nc, std::max(8, (d.nc + 1) / 2));
     if (best > 0 && (best >= std::min(d.cap, need) || forced_tile_cap)) {
       fill_layout_tile(d, b->lay, per_cta, best, tctas, pis);

@@ -17,6 +17,7 @@ struct Ctx
   double* kt2;     // second dense coefficient vector (global dual residual)
   double* W;       // P^-1 B^T, n x ldb (L2 workspace; only needed to form G)
   int ldb, ldn;    // leading dimensions of Bt and Pi (even)
+  int m;           // rows of B = [A_s; C_s; box rows]: ne + nc
   const double *Hs, *Cs;        // scaled matrices of this QP (global)
   const double *Hm, *Am, *Cm;   // model matrices (global, unscaled)
   // vectors
@@ -832,7 +833,7 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
   }
   apply_Pinv(c, b1, v_t1);
   // B t for every row of [A_s; C_s] at once (Bt = B^T), then pick the slots
-  axpy_pass(c, c.Bt, c.ldb, n, v_t1, ne + c.ni, c.kt, nullptr, 1.0);
+  axpy_pass(c, c.Bt, c.ldb, n, v_t1, c.m, c.kt, nullptr, 1.0);
   _Pragma("unroll 1") for (int s = threadIdx.x; s < ns; s += NT) v_s1[s] = c.kt[row_id(c, s)] - b2[s];
   __syncthreads();
   tsym_mv(c, c.Si, v_s1, os, ns);
@@ -842,7 +843,7 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
     double lam = 0.0;
     if (id < ne) {
       lam = os[id];
-    } else if (id < ne + c.ni) {
+    } else if (id < c.m) {
       const int s = c.cons_slot[id - ne];
       if (s >= 0) lam = os[s];
     }
@@ -1018,8 +1019,16 @@ __device__ __noinline__ void build_Bt(Ctx& c)
     const double* row = (r < ne) ? c.As + (size_t)r * n : c.Cs + (size_t)(r - ne) * n;
     for (int j = lane; j < n; j += 32) c.Bt[(size_t)j * c.ldb + r] = row[j];
   }
-  if (c.ldb > nr) {
-    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) c.Bt[(size_t)j * c.ldb + nr] = 0.0;
+  if (c.box) {
+    // box rows are the scaled unit vectors i_s[k] e_k (solver.hpp:74-81): materialised, so that
+    // every product below treats the n_in + n inequality rows alike
+    PQP_VECS(c);
+    for (int j = warp; j < n; j += NW) {
+      for (int k = lane; k < n; k += 32) c.Bt[(size_t)j * c.ldb + nr + k] = (k == j) ? v_is[j] : 0.0;
+    }
+  }
+  if (c.ldb > c.m) {
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) c.Bt[(size_t)j * c.ldb + c.m] = 0.0;
   }
   __syncthreads();
 }
@@ -1028,7 +1037,7 @@ __device__ __noinline__ void build_Bt(Ctx& c)
 // read as G[max][min]). Depends on H_s, rho, A_s, C_s only: once per QP.
 __device__ __noinline__ void build_G(Ctx& c)
 {
-  const int n = c.n, m = c.ne + c.ni;
+  const int n = c.n, m = c.m;
   gemm_tn(c.Pi, c.ldn, c.Bt, c.ldb, n, n, m, c.W, c.ldb, false); // W = Pi^T Bt (Pi symmetric)
   gemm_tn(c.Bt, c.ldb, c.W, c.ldb, n, m, m, c.G, c.ldb, true);   // G = Bt^T W, lower block triangle
 }
@@ -1067,7 +1076,7 @@ __device__ __noinline__ double kkt_residual(const Ctx& c, const Scal& sc, bool f
   PQP_VECS(c);
   const int n = c.n, ne = c.ne, ns = c.ns;
   axpy_pass(c, c.Hs, n, n, v_dx, n, v_hdx, nullptr, 1.0);                    // H dx (H symmetric)
-  axpy_pass(c, c.Bt, c.ldb, n, v_dx, ne + c.ni, v_adx, nullptr, 1.0);        // [A dx; C dx] (adx, cdx contiguous)
+  axpy_pass(c, c.Bt, c.ldb, n, v_dx, c.m, v_adx, nullptr, 1.0);        // [A dx; C dx] (adx, cdx contiguous)
   // A^T dy + C_J^T dz_J is B^T lam of the solve that produced (dx, ds) (first call) or of the
   // refinement step just added to it: no third pass over the constraint rows
   double m = 0;
@@ -1217,7 +1226,7 @@ __device__ __noinline__ void global_passes(Ctx& c, bool primal, bool dual)
     __syncthreads();
     bt_dot(c, c.kt, c.kt2, v_t2, nullptr, 1.0, nullptr, v_t3);
   }
-  if (primal) axpy_pass(c, c.Bt, c.ldb, n, v_x, ne + ni, v_se, nullptr, 1.0); // [A x; C x] (se, rup contiguous)
+  if (primal) axpy_pass(c, c.Bt, c.ldb, n, v_x, c.m, v_se, nullptr, 1.0); // [A x; C x] (se, rup contiguous)
 }
 
 __device__ __noinline__ void global_primal_residual(Ctx& c, const Scal& sc, const pqp_settings& S, Glob& g)
@@ -1567,6 +1576,9 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
       c.act_up[j] = 0;
       c.act_low[j] = 0;
     }
+    if (c.box) {
+      _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_is[j] = P.is[(size_t)q * n + j];
+    }
     _Pragma("unroll 1") for (int j = tid; j < n + ne + nc; j += NT) v_delta[j] = P.delta[(size_t)q * (n + ne + nc) + j];
     if (tid == 0) {
       c.c_scale = P.c[q];
@@ -1772,7 +1784,7 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
         int nq = 0;
         _Pragma("unroll 1") for (int id = tid; id < c.ldb; id += NT) {
           double zq = 0.0;
-          if (id >= ne && id < ne + ni && c.cons_slot[id - ne] < 0) zq = v_z[id - ne];
+          if (id >= ne && id < c.m && c.cons_slot[id - ne] < 0) zq = v_z[id - ne];
           c.kt[id] = zq;
           nq |= (zq != 0.0) ? 1 : 0;
         }
@@ -2091,7 +2103,8 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArg
     c.pi_smem = 0;
     c.si_cap = L.si_cap;
     c.uv_ld = ((A.d.n > L.si_cap ? A.d.n : L.si_cap) + 2) & ~1;
-    c.ldb = (A.d.ne + A.d.ni + 1) & ~1;
+    c.m = A.d.ne + A.d.nc;
+    c.ldb = (c.m + 1) & ~1;
     c.ldn = (A.d.n + 1) & ~1;
     c.overflow = 0;
     double* ws = A.ws + (size_t)blockIdx.x * (size_t)L.ws_doubles;

@@ -388,3 +388,15 @@ def test_pipelined_init_solve_equals_single_launch(px, monkeypatch):
     for k in ("x", "y", "z"):
         assert np.array_equal(r_pipe[k], r_one[k]) and np.array_equal(r_pipe2[k], r_one[k])
     assert np.array_equal(r_pipe["info"]["iter"], r_one["info"]["iter"])
+
+
+def test_tile_kernel_box_constraints(px, oracle):
+    """Box constraints in the tile kernel (n even: box rows materialised in the
+    transposed constraint copy): oracle-identical iteration counts and solution."""
+    for seed in range(6):
+        d = oracle.generate_qp("box_benchmark", seed, 20, 6, 10, sparsity=0.5)
+        qp = gpu_solve(px, d, box=True)
+        _, ro = oracle_solve(oracle, d, box=True)
+        assert qp.results.z.shape[0] == 10 + 20
+        assert_parity(d, qp.results, ro)
+        assert qp.results.info.iter == ro.info.iter and qp.results.info.iter_ext == ro.info.iter_ext
