@@ -124,6 +124,18 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def best_thread_count(batch, candidates):
+    """The CPU arm gets the thread count that serves it best on this host: every logical CPU, or
+    half of them (the reference's own default, parallel/qp_solve.hpp:45-49; SMT siblings can hurt)."""
+    best_t, best_time = None, None
+    for t in candidates:
+        batch.solve(t)  # page-in / thread start
+        dt = batch.solve(t)
+        if best_time is None or dt < best_time:
+            best_t, best_time = t, dt
+    return best_t
+
+
 def cpu_baseline(sample, reps, threads=0):
     """The oracle (C++ restatement of the reference, kind "port") on the host
     cores: OpenMP schedule(dynamic) over QPs with all threads, batch already
@@ -131,13 +143,14 @@ def cpu_baseline(sample, reps, threads=0):
     from oracle import oracle as O
 
     O.build()
-    T = threads or host_threads()
     st = generate(0, sample, O.generate_qp)
     b = O.OracleBatch(sample, N_DIM, N_EQ, N_IN)
     for i in range(sample):
         q = b[i]
         q.set(eps_abs=EPS_ABS, eps_rel=0, initial_guess=O.NO_INITIAL_GUESS)
         q.init(**{k: st[k][i] for k in KEYS})
+    H = host_threads()
+    T = threads or best_thread_count(b, sorted({H, max(1, H // 2)}, reverse=True))
     b.solve(T)  # warm-up
     b.counters(reset=True)
     best = None
@@ -162,13 +175,14 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
 
     O.build()
-    T = host_threads()
     st = generate(0, sample, O.generate_qp)
     b = O.OracleBatch(sample, N_DIM, N_EQ, N_IN)
     for i in range(sample):
         q = b[i]
         q.set(eps_abs=EPS_ABS, eps_rel=0, initial_guess=O.NO_INITIAL_GUESS)
         q.init(**{k: st[k][i] for k in KEYS})
+    H = host_threads()
+    T = best_thread_count(b, sorted({H, max(1, H // 2)}, reverse=True))
     for _ in range(args.warmup):
         b.solve(T)
     t0 = time.perf_counter()
