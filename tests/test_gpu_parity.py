@@ -400,3 +400,33 @@ def test_tile_kernel_box_constraints(px, oracle):
         assert qp.results.z.shape[0] == 10 + 20
         assert_parity(d, qp.results, ro)
         assert qp.results.info.iter == ro.info.iter and qp.results.info.iter_ext == ro.info.iter_ext
+
+
+def test_maros_meszaros_small_problems(px, oracle):
+    """The reference's Maros-Meszaros acceptance test (dense_maros_meszaros.cpp:87-165) on the
+    28 small problems of tests/golden/maros_meszaros_small.npz, through the C-ABI: same status
+    and objective as the oracle, the reference's residual criteria, and zero iterations on a
+    warm restart from the previous result."""
+    from test_oracle_maros import EPS as MEPS, check_reference_criteria, problems
+
+    for name, d in problems():
+        n, ne, ni = d["H"].shape[0], d["A"].shape[0], d["C"].shape[0]
+        qo = oracle.OracleQP(n, ne, ni, dense_backend=oracle.BACKEND_AUTOMATIC)
+        qo.set(eps_abs=MEPS, eps_rel=0.0, eps_primal_inf=1e-12, eps_dual_inf=1e-12)
+        qo.init(**d)
+        ro = qo.solve()
+        qp = px.dense.QP(n, ne, ni, False, px.HessianType.Dense, px.DenseBackend.Automatic)
+        qp.settings.eps_abs = MEPS
+        qp.settings.eps_rel = 0
+        qp.settings.eps_primal_inf = 1e-12
+        qp.settings.eps_dual_inf = 1e-12
+        qp.init(d["H"], d["g"], d["A"], d["b"], d["C"], d["l"], d["u"])
+        qp.solve()
+        r = qp.results
+        assert int(r.info.status) == ro.info.status == 0, name
+        check_reference_criteria(d, r.x, r.y, r.z)
+        obj_o = 0.5 * ro.x @ d["H"] @ ro.x + d["g"] @ ro.x
+        assert abs(r.info.objValue - obj_o) <= 1e-6 * max(1.0, abs(obj_o)), name
+        qp.settings.initial_guess = px.InitialGuess.WARM_START_WITH_PREVIOUS_RESULT
+        qp.solve()
+        assert qp.results.info.iter == 0, name
