@@ -14,8 +14,10 @@ eps_rel=0, NO_INITIAL_GUESS). A "step" is one solve_in_parallel over the whole
 every rank owns its own 1024 QPs, no collective in the data path.
 
 `value`   : QPs/s with inputs resident in HBM, CUDA-event timed on the launching stream.
-`e2e`     : QPs/s through the public API with HOST (pinned) inputs: H2D copy + init
-            (Ruiz set-up kernel) + solve + D2H of x, y, z, se, si, info, every step.
+`e2e`     : QPs/s through the public API with HOST (pinned) inputs, every step: init (chunked H2D
+            upload, a progress word behind each chunk) + solve (ONE persistent kernel that waits
+            for each QP's inputs, runs its Ruiz equilibration and solves it) + D2H of x, y, z,
+            se, si, info. PQP_E2E=plain|chunks selects the older separate-launch pipelines.
 `roofline`: algorithmic bytes (SURVEY.md section 8(d)(ii) streamed-operand model,
             evaluated from the oracle's operation counters on a sample of the
             same workload) / measured solve-kernel time, against the measured
@@ -353,6 +355,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"BatchQP {B} random dense QPs per GPU, n={n} n_eq={n_eq_str()} n_in={ni}, fp64, eps_abs=1e-9 eps_rel=0 NO_INITIAL_GUESS (BASELINE.json configs[1]; generator of benchmark/timings-parallel.cpp)",
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"batch sharded over {world} GPU(s), no collective in the iteration",
+                       "e2e_mode": os.environ.get("PQP_E2E", "fused") + " (init uploads, the solve kernel equilibrates + solves each QP as its inputs arrive)",
                        "l2": "inputs larger than L2 (scaled+model data %.0f MB per GPU per step)" % (2 * h2d_bytes / 1e6)},
             "e2e": {"value": e2e_value, "unit": "QPs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches),

@@ -48,6 +48,7 @@ struct QpFlags
 
 #define PQP_UPLOAD_CHUNKS 8
 #define PQP_CSTREAMS 4 // compute streams the chunks of a pipelined init + solve rotate over
+#define PQP_FEED_CHUNKS 16 // upload chunks of the fused feed (a 4-byte progress word follows each)
 
 struct pqp_batch
 {
@@ -85,6 +86,14 @@ struct pqp_batch
   int64_t launches = 0;
   int64_t overflow_retries = 0;
   bool solve_pending = false;
+  // Fused feed: a whole-batch init() / update() only uploads; the equilibration is done by the persistent solve
+  // kernel (the CTA that pops a QP sets it up, then solves it), gated per QP on the progress of the upload.
+  int deferred = 0;            // 0: nothing pending; else PqpSolveArgs::fused_setup code of the pending set-up
+  bool deferred_gated = false; // the upload runs on copy_stream and announces its progress through d_ready
+  bool fused_ok = false;       // the solve kernel's shared memory holds the set-up scratch
+  int32_t* d_ready = nullptr;  // [0] QPs uploaded so far, [1] abort flag
+  int32_t* h_ready = nullptr;  // pinned: cumulative QP count behind each upload chunk
+  cudaEvent_t ev_feed = nullptr;
 };
 
 namespace {
@@ -564,6 +573,21 @@ join_cstreams(pqp_batch* b)
   return 0;
 }
 
+// A deferred set-up that the next call cannot fuse (anything but a solve of the whole batch): run it now.
+int
+flush_deferred(pqp_batch* b)
+{
+  if (!b->deferred) return 0;
+  const int code = b->deferred;
+  b->deferred = 0;
+  if (b->deferred_gated) {
+    CUDA_TRY(cudaEventRecord(b->ev_feed, b->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_feed, 0));
+    b->deferred_gated = false;
+  }
+  return launch_setup(b, 0, b->B, (code & 1) != 0, (code & 4) != 0);
+}
+
 int
 do_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const double* g, const double* A, const double* b_, const double* C, const double* l, const double* u, const double* l_box, const double* u_box, int compute_preconditioner,
         const double* rho, const double* mu_eq, const double* mu_in, const double* manual_eig, bool dev_ptrs)
@@ -587,18 +611,11 @@ do_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const doubl
   }
   if (int rc = zero_results_runs(b, first, need_zero)) return rc;
   const int64_t n = d.n, ne = d.ne, ni = d.ni;
-  // Host inputs of a large range are uploaded in chunks on a second stream; the set-up kernel of
-  // chunk k runs while chunk k+1 is still crossing PCIe.
-  const int nchunks = (!dev_ptrs && count >= 256) ? (int)std::min<int64_t>(PQP_UPLOAD_CHUNKS, count / 128) : 1;
-  b->nchunks_pending = 0;
-  if (nchunks > 1) {
-    CUDA_TRY(cudaEventRecord(b->ev_main, b->stream)); // uploads must not overtake kernels still reading the buffers
-    CUDA_TRY(cudaStreamWaitEvent(b->copy_stream, b->ev_main, 0));
-    for (int j = 0; j < PQP_CSTREAMS; ++j) CUDA_TRY(cudaStreamWaitEvent(b->cstream[j], b->ev_main, 0));
-  }
-  for (int k = 0; k < nchunks; ++k) {
-    const int64_t f = first + count * k / nchunks, e = first + count * (k + 1) / nchunks, cnt = e - f, o = f - first;
-    cudaStream_t st = nchunks > 1 ? b->copy_stream : b->stream;
+  const bool whole = first == 0 && count == b->B && count > 0;
+  const char* mode_env = std::getenv("PQP_E2E"); // "fused" (default) | "chunks" (per-chunk set-up + solve launches) | "plain"
+  const std::string mode = mode_env ? mode_env : "fused";
+  auto upload = [&](int64_t f, int64_t cnt, cudaStream_t st) -> int {
+    const int64_t o = f - first;
     auto at = [&](const double* src, int64_t per) { return src ? src + o * per : nullptr; };
     if (int rc = copy_in(b, b->p.H, at(H, n * n), f, cnt, n * n, dev_ptrs, st)) return rc;
     if (int rc = copy_in(b, b->p.g, at(g, n), f, cnt, n, dev_ptrs, st)) return rc;
@@ -611,6 +628,49 @@ do_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const doubl
       if (int rc = copy_in(b, b->p.l_box, at(l_box, n), f, cnt, n, dev_ptrs, st)) return rc;
       if (int rc = copy_in(b, b->p.u_box, at(u_box, n), f, cnt, n, dev_ptrs, st)) return rc;
     }
+    return 0;
+  };
+  b->nchunks_pending = 0;
+  if (whole && b->fused_ok && mode == "fused") {
+    // Fused feed: upload only. The persistent solve kernel equilibrates each QP right before solving it and,
+    // for host inputs, starts while later chunks are still crossing PCIe (gated on d_ready).
+    if (b->deferred && b->deferred_gated) { // an unconsumed feed: its uploads must land before the new ones
+      CUDA_TRY(cudaEventRecord(b->ev_feed, b->copy_stream));
+      CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_feed, 0));
+    }
+    b->deferred = compute_preconditioner ? 1 : (2 | 4);
+    b->deferred_gated = false;
+    if (!dev_ptrs && count >= 256) {
+      const int nchunks = (int)std::min<int64_t>(PQP_FEED_CHUNKS, count / 64);
+      CUDA_TRY(cudaEventRecord(b->ev_main, b->stream)); // uploads must not overtake kernels still reading the buffers
+      CUDA_TRY(cudaStreamWaitEvent(b->copy_stream, b->ev_main, 0));
+      CUDA_TRY(cudaMemsetAsync(b->d_ready, 0, 2 * sizeof(int32_t), b->copy_stream));
+      CUDA_TRY(cudaEventRecord(b->ev_feed, b->copy_stream));
+      CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_feed, 0)); // no kernel may see the progress word of the previous feed
+      for (int k = 0; k < nchunks; ++k) {
+        const int64_t f = count * k / nchunks, e = count * (k + 1) / nchunks;
+        if (int rc = upload(f, e - f, b->copy_stream)) return rc;
+        b->h_ready[k] = (int32_t)e;
+        CUDA_TRY(cudaMemcpyAsync(b->d_ready, b->h_ready + k, sizeof(int32_t), cudaMemcpyHostToDevice, b->copy_stream));
+      }
+      b->deferred_gated = true;
+    } else if (int rc = upload(first, count, b->stream)) {
+      return rc;
+    }
+    return 0;
+  }
+  if (int rc = flush_deferred(b)) return rc;
+  // Host inputs of a large range are uploaded in chunks on a second stream; the set-up kernel of
+  // chunk k runs while chunk k+1 is still crossing PCIe.
+  const int nchunks = (!dev_ptrs && count >= 256 && mode != "plain") ? (int)std::min<int64_t>(PQP_UPLOAD_CHUNKS, count / 128) : 1;
+  if (nchunks > 1) {
+    CUDA_TRY(cudaEventRecord(b->ev_main, b->stream)); // uploads must not overtake kernels still reading the buffers
+    CUDA_TRY(cudaStreamWaitEvent(b->copy_stream, b->ev_main, 0));
+    for (int j = 0; j < PQP_CSTREAMS; ++j) CUDA_TRY(cudaStreamWaitEvent(b->cstream[j], b->ev_main, 0));
+  }
+  for (int k = 0; k < nchunks; ++k) {
+    const int64_t f = first + count * k / nchunks, e = first + count * (k + 1) / nchunks, cnt = e - f;
+    if (int rc = upload(f, cnt, nchunks > 1 ? b->copy_stream : b->stream)) return rc;
     cudaStream_t cs = b->stream;
     if (nchunks > 1) {
       cs = b->cstream[k % PQP_CSTREAMS];
@@ -624,7 +684,7 @@ do_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const doubl
   if (nchunks > 1) {
     if (int rc = join_cstreams(b)) return rc;
     // the whole batch, freshly initialised: a solve() issued next may run chunk by chunk
-    if (first == 0 && count == b->B && b->ws_slot_doubles > 0) b->nchunks_pending = nchunks;
+    if (whole && b->ws_slot_doubles > 0) b->nchunks_pending = nchunks;
   }
   return 0;
 }
@@ -637,7 +697,7 @@ fill_vec(std::vector<double>& v, double val)
 
 // upload the per-QP launch parameters and enqueue one persistent solve kernel
 int
-enqueue_solve(pqp_batch* b, cudaStream_t st, const PqpLayout& lay, int grid, int64_t first = 0, int64_t count = -1, int slot = 0, bool timed = true)
+enqueue_solve(pqp_batch* b, cudaStream_t st, const PqpLayout& lay, int grid, int64_t first = 0, int64_t count = -1, int slot = 0, bool timed = true, int fused_code = 0, int32_t* ready = nullptr)
 {
   if (count < 0) count = b->B;
   CUDA_TRY(cudaMemcpyAsync(b->p.params + first, b->hparams.data() + first, sizeof(PqpQpParams) * (size_t)count, cudaMemcpyHostToDevice, st));
@@ -656,6 +716,15 @@ enqueue_solve(pqp_batch* b, cudaStream_t st, const PqpLayout& lay, int grid, int
   a.prof = b->prof;
   if (const char* e = std::getenv("PQP_DEBUG_TRACE")) a.dbg_qp = std::atoi(e);
   if (const char* e = std::getenv("PQP_WATCHDOG_MS")) a.watchdog_ns = 1000000ull * (unsigned long long)std::atoll(e);
+  a.fused_setup = fused_code;
+  a.ready = ready;
+  {
+    // smallest per-QP array the upload writes, in bytes: QPs that close together can share a cache line
+    int64_t mn = (int64_t)b->d.n;
+    if (b->d.ne > 0) mn = std::min<int64_t>(mn, b->d.ne);
+    if (b->d.ni > 0) mn = std::min<int64_t>(mn, b->d.ni);
+    a.feed_margin = (int32_t)((128 + 8 * mn - 1) / (8 * mn));
+  }
   if (timed) CUDA_TRY(cudaEventRecord(b->ev2, st));
   int rc = pqp_launch_solve(&a, grid, st);
   if (rc != 0) return fail(PQP_ECUDA, std::string("solve kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
@@ -805,6 +874,11 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
   rc |= dev_alloc(b, &p.info, B * PQP_INFO_DOUBLES);
   rc |= dev_alloc(b, &p.params, B);
   rc |= dev_alloc(b, &b->counter, PQP_CSTREAMS + 1);
+  rc |= dev_alloc(b, &b->d_ready, 2);
+  if (cudaHostAlloc((void**)&b->h_ready, sizeof(int32_t) * (PQP_FEED_CHUNKS + 2), cudaHostAllocDefault) != cudaSuccess) {
+    b->h_ready = nullptr;
+    rc |= fail(PQP_ECUDA, "cudaHostAlloc failed");
+  }
   if (rc != 0) {
     pqp_batch_destroy(b);
     return nullptr;
@@ -834,7 +908,8 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
     info_defaults(b->hinfo[i], nullptr, b->backend);
     b->hinfo[i].status = PQP_NOT_RUN;
   }
-  bool aux_ok = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming) == cudaSuccess;
+  bool aux_ok = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&b->ev_feed, cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < PQP_UPLOAD_CHUNKS; ++k) aux_ok = aux_ok && cudaEventCreateWithFlags(&b->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < PQP_CSTREAMS; ++k)
     aux_ok = aux_ok && cudaStreamCreateWithFlags(&b->cstream[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&b->ev_cdone[k], cudaEventDisableTiming) == cudaSuccess;
@@ -848,6 +923,8 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
     pqp_batch_destroy(b);
     return nullptr;
   }
+  // the fused feed runs the set-up inside the solve kernel, in the shared memory of the primary layout
+  b->fused_ok = (int64_t)sizeof(double) * b->lay.smem_doubles >= pqp_setup_smem_bytes(d.n, d.ne, d.ni, d.nc);
   // persistent grids: resident CTAs per SM x SM count, never more than the batch
   {
     int sms = 0;
@@ -899,6 +976,8 @@ pqp_batch_destroy(pqp_batch* b)
   if (b->ev2) cudaEventDestroy(b->ev2);
   if (b->ev3) cudaEventDestroy(b->ev3);
   if (b->ev_main) cudaEventDestroy(b->ev_main);
+  if (b->ev_feed) cudaEventDestroy(b->ev_feed);
+  if (b->h_ready) cudaFreeHost(b->h_ready);
   for (int k = 0; k < PQP_UPLOAD_CHUNKS; ++k)
     if (b->ev_chunk[k]) cudaEventDestroy(b->ev_chunk[k]);
   for (int k = 0; k < PQP_CSTREAMS; ++k) {
@@ -972,6 +1051,7 @@ pqp_batch_update(pqp_batch* b, int64_t first, int64_t count, const double* H, co
   if (!d.box && (l_box || u_box))
     return fail(PQP_EINVAL, "wrong model setup: the QP object is designed without box constraints, but the update includes lower or upper box inequalities.");
   CUDA_TRY(cudaSetDevice(b->device));
+  if (int rc = flush_deferred(b)) return rc;
   b->nchunks_pending = 0; // work enqueued on the main stream from here on: the next solve is a single launch
   // wrapper.hpp:743-746: update before init == init (per QP); handle the
   // common case where the whole range is in the same state.
@@ -1012,6 +1092,14 @@ pqp_batch_update(pqp_batch* b, int64_t first, int64_t count, const double* H, co
     if (int rc = copy_in(b, b->p.u_box, u_box, first, count, n, false)) return rc;
   }
   // EXECUTE recomputes the scaling, KEEP re-applies the stored one
+  {
+    const char* mode_env = std::getenv("PQP_E2E");
+    if (first == 0 && count == b->B && count > 0 && b->fused_ok && (!mode_env || std::string(mode_env) == "fused")) {
+      b->deferred = update_preconditioner ? 1 : 2; // done by the next solve's persistent kernel, QP by QP
+      b->deferred_gated = false;
+      return 0;
+    }
+  }
   return launch_setup(b, first, count, update_preconditioner != 0, false);
 }
 
@@ -1075,7 +1163,26 @@ pqp_batch_solve_async(pqp_batch* b, void* stream_)
   }
   bool all_active = true;
   for (int64_t i = 0; i < b->B; ++i) all_active = all_active && b->hparams[i].active;
-  if (!stream_ && b->nchunks_pending > 1 && all_active && !b->prof && !b->dbg && !std::getenv("PQP_NO_PIPELINE")) {
+  if (b->deferred && (b->prof || b->dbg)) {
+    if (int rc = flush_deferred(b)) return rc;
+  }
+  if (b->deferred) {
+    // fused feed: one persistent launch that equilibrates and solves, consuming QPs as their inputs arrive
+    const int code = b->deferred;
+    const bool gated = b->deferred_gated;
+    b->deferred = 0;
+    b->deferred_gated = false;
+    b->setup_timed = false; // the set-up is part of the solve kernel: solve_ms covers both
+    if (st != b->stream) { // uploads / memsets of init() were enqueued on the batch's own stream
+      CUDA_TRY(cudaEventRecord(b->ev_main, b->stream));
+      CUDA_TRY(cudaStreamWaitEvent(st, b->ev_main, 0));
+    }
+    if (int rc = enqueue_solve(b, st, b->lay, b->grid, 0, -1, 0, true, code, gated ? b->d_ready : nullptr)) return rc;
+    if (gated) { // later work on this stream must also see the complete upload
+      CUDA_TRY(cudaEventRecord(b->ev_feed, b->copy_stream));
+      CUDA_TRY(cudaStreamWaitEvent(st, b->ev_feed, 0));
+    }
+  } else if (!stream_ && b->nchunks_pending > 1 && all_active && !b->prof && !b->dbg && !std::getenv("PQP_NO_PIPELINE")) {
     // pipelined: one launch per uploaded chunk, on the stream that runs the chunk's set-up kernel
     CUDA_TRY(cudaEventRecord(b->ev2, b->cstream[0])); // solve_ms then spans first chunk start .. last chunk end
     for (int k = 0; k < b->nchunks_pending; ++k) {
@@ -1222,6 +1329,9 @@ pqp_batch_results_device(pqp_batch* b, double** x, double** y, double** z, doubl
 int
 pqp_batch_scaled(pqp_batch* b, int64_t index, double* H, double* g, double* A, double* b_, double* C, double* u, double* l, double* delta, double* c)
 {
+  if (b) {
+    if (int rc = flush_deferred(b)) return rc;
+  }
   if (int rc = check_range(b, index, 1)) return rc;
   CUDA_TRY(cudaSetDevice(b->device));
   CUDA_TRY(cudaStreamSynchronize(b->stream));

@@ -122,6 +122,14 @@ struct PqpSolveArgs
   int32_t dbg_cap;
   long long* prof;   // optional per-phase cycle counters (12 entries), NULL = off
   unsigned long long watchdog_ns; // 0 = off; per-QP time budget after which the QP is abandoned (status MAX_ITER_REACHED)
+  // Fused feed (end-to-end path: init() from host buffers directly followed by solve()):
+  int32_t* ready;      // NULL: every input is resident. Else ready[0] = number of QPs of this launch whose inputs have
+                       // arrived (written by a 4-byte copy behind each uploaded chunk), ready[1] = abort flag
+  int32_t fused_setup; // 0: the scaled data are ready; bit 0: run Ruiz (EXECUTE), bit 1: re-apply the stored scaling,
+                       // bit 2: reset delta / c first (IDENTITY) -- the CTA that pops a QP equilibrates it, then solves it
+  int32_t feed_margin; // a QP is consumed once the inputs of the `feed_margin` QPs after it have arrived too: no 128-byte
+                       // line of its arrays can then still be changed by the upload (a stale copy in an SM's L1 would
+                       // otherwise survive until that SM solves the neighbour)
 };
 
 struct PqpSetupArgs
@@ -140,6 +148,7 @@ extern "C" {
 int pqp_launch_setup(const PqpSetupArgs* a, void* stream);
 int pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream);
 int pqp_solve_max_smem(void);
+int64_t pqp_setup_smem_bytes(int n, int ne, int ni, int nc);
 #ifdef __cplusplus
 }
 #endif

@@ -1172,17 +1172,22 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
   // A bordering step costs two passes over S^-1; a rebuild from G costs (ns+nadd)/4 block
   // sweeps of the same size. Many simultaneous additions (the first Newton steps) are
   // therefore registered at once and S^-1 is re-formed from the Gram matrix.
-  if (!c.si_valid || (nadd >= 8 && 2 * nadd >= (c.ns + nadd + 3) / 4)) {
-    if (c.ns + nadd > c.si_cap) {
+  // c.ns / c.si_valid decide a block-uniform branch: every thread reads them ONCE, and thread 0 may only change
+  // them after a barrier (a warp that is late here - e.g. on an instruction-cache miss - would otherwise see the
+  // new slot count, take the other branch and desynchronise the CTA's barriers)
+  const int base = c.ns;
+  const bool rebuild = !c.si_valid || (nadd >= 8 && 2 * nadd >= (base + nadd + 3) / 4);
+  if (rebuild) {
+    if (base + nadd > c.si_cap) {
       if (threadIdx.x == 0) c.overflow = 1;
       __syncthreads();
     } else {
-      const int base = c.ns;
       _Pragma("unroll 1") for (int k = threadIdx.x; k < nadd; k += NT) {
         const int cons = c.list1[k];
         c.slot_cons[base + k] = cons;
         c.cons_slot[cons] = base + k;
       }
+      __syncthreads();
       if (threadIdx.x == 0) c.ns = base + nadd;
       __syncthreads();
       rebuild_Si_from_G(c, sc.mu_eq, sc.mu_in);
@@ -1533,7 +1538,10 @@ __device__ void dbg_write(const PqpSolveArgs& A, int q, int& pos, double a, doub
 // ---------------------------------------------------------------------------
 // one QP, start to finish: dense/solver.hpp:1088-1843
 // ---------------------------------------------------------------------------
-__device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
+#ifndef PQP_SOLVE_ONE_ATTR
+#define PQP_SOLVE_ONE_ATTR
+#endif
+__device__ PQP_SOLVE_ONE_ATTR void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
 {
   PQP_VECS(c);
   const PqpQpParams& prm = A.p.params[q];
@@ -2090,10 +2098,22 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
 
 extern __shared__ __align__(16) double smem_dyn[];
 
-__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArgs A)
+// FUSED: the feed gate + set-up of the end-to-end path are compiled in (a separate instantiation keeps the
+// register allocation of the plain solve kernel untouched)
+template<int FUSED>
+__device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A)
 {
   __shared__ Ctx c;
   __shared__ int cur_q;
+  __shared__ setupk::FeedArgs feed_args;
+  if (FUSED && threadIdx.x == 0) {
+    feed_args.d = A.d;
+    feed_args.p = A.p;
+    feed_args.ready = A.ready;
+    feed_args.batch = A.batch;
+    feed_args.fused_setup = A.fused_setup;
+    feed_args.feed_margin = A.feed_margin;
+  }
   __shared__ long long prof_sh[PH_COUNT];
   const PqpLayout& L = A.lay;
   if (threadIdx.x == 0) {
@@ -2186,9 +2206,13 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArg
   while (true) {
     if (threadIdx.x == 0) cur_q = atomicAdd(A.counter, 1);
     __syncthreads();
-    const int q = A.first + cur_q; // this launch owns the QPs [first, first + batch)
+    const int cq = cur_q;
+    const int q = A.first + cq; // this launch owns the QPs [first, first + batch)
     __syncthreads();
-    if (cur_q >= A.batch) break;
+    if (cq >= A.batch) break;
+    if (FUSED && (A.ready || A.fused_setup)) {
+      if (!setupk::feed_and_setup(&feed_args, cq, q, smem_dyn)) continue;
+    }
     if (!A.p.params[q].active) continue;
     solve_one(c, A, q);
   }
@@ -2197,3 +2221,17 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArg
   }
 }
 
+// Plain launch: parameters by value, exactly the kernel the device-resident path has always run.
+#ifdef PQP_PLAIN_GC
+__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(const __grid_constant__ PqpSolveArgs A)
+#else
+__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArgs A)
+#endif
+{
+  solve_kernel_body<0>(A);
+}
+// Fused feed: __grid_constant__ lets the non-inlined set-up read the parameters in place.
+__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel_fused(const __grid_constant__ PqpSolveArgs A)
+{
+  solve_kernel_body<1>(A);
+}

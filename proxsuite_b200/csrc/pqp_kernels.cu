@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <cstdlib>
 
 #define NT PQP_NT
 #define NW PQP_NW
@@ -34,6 +35,18 @@
 // the two inverse blocks are in shared memory (the layout chosen whenever they
 // fit), which lets ptxas emit LDS/STS with 32-bit addresses instead of generic
 // LD/ST; `genk` makes no assumption (large problems spilling to global memory).
+namespace setupk {
+// dims / pointers are handed over through a shared-memory copy: taking the address of the kernel parameter
+// itself makes the compiler keep the whole parameter block addressable, which costs the solve part registers
+struct FeedArgs
+{
+  PqpDims d;
+  PqpBatchPtrs p;
+  int32_t* ready;
+  int32_t batch, fused_setup, feed_margin;
+};
+__device__ bool feed_and_setup(const FeedArgs* F, int cur_q, int q, double* sm);
+}
 #define PQP_SM(p) __builtin_assume(__isShared(p))
 namespace fastk {
 #include "pqp_solver_body.inl"
@@ -48,97 +61,194 @@ namespace genk {
 }
 #undef PQP_SM
 
-namespace {
+namespace setupk {
 using genk::warp_max;
 using genk::warp_sum;
 // ---------------------------------------------------------------------------
-// Set-up kernel: model -> scaled copies, bound clamping, Ruiz equilibration.
+// Set-up of one QP: model -> scaled copies, bound clamping, Ruiz equilibration.
 // helpers.hpp:573-666, ruiz.hpp:31-311 (execute) and :425-511 (re-apply).
-// One CTA per QP, operating on the L2-resident scaled arrays in place.
+// One CTA per QP, operating on the scaled arrays in place (L2 resident).
+//
+// The reference makes two passes over H, A, C per Ruiz iteration (norms, then
+// scaling). Here the scaling pass of iteration k also accumulates the column /
+// row infinity norms of the values it writes, which ARE the norms iteration
+// k + 1 needs, and the very first norms come out of the model -> scaled copy:
+// one read-modify-write pass per iteration, same numbers bit for bit.
 // ---------------------------------------------------------------------------
-#define SETUP_CH 8 // columns per lane per chunk (32 * 8 = 256 columns)
 
 struct SetupCtx
 {
   int n, ne, ni, nc, box, hess;
+  int cstride;    // columns of one block: min(256, n rounded up to 32)
   double *Hs, *As, *Cs, *gs, *bs, *us, *ls, *is, *delta;
   double *dcur;   // n + ne + nc
-  double *colmax; // NW * 256
+  double *colmax; // NW * cstride per-warp partial column maxima of one column block
   double *rowmax; // ne + ni
+  double *colH;   // n : column norms of H_s (dense)
+  double *colAC;  // n : column norms of [A_s; C_s]
   double *red;    // 64
 };
 
-// column / row infinity norms of one row-major matrix, accumulated into
-// colmax (per-warp partials) and rowmax
-__device__ void setup_norms(const SetupCtx& s, const double* M, int rows, int cb, int cw, double* cm /*regs*/, double* rowmax_out)
+__host__ __device__ inline int setup_cstride(int n)
+{
+  const int r = (n + 31) & ~31;
+  return r < 256 ? r : 256;
+}
+__host__ __device__ inline size_t setup_smem_doubles(int n, int ne, int ni, int nc)
+{
+  return (size_t)(n + ne + nc) + (size_t)NW * setup_cstride(n) + (size_t)(ne + ni) + 2 * (size_t)n + 64;
+}
+
+// combine the per-warp partial column maxima of the block [cb, cb + cw) into out[cb ..]
+template<int NCH>
+__device__ __forceinline__ void setup_combine_cols(const SetupCtx& s, const double* cm, int cb, int cw, double* out)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cs = s.cstride;
+#pragma unroll
+  for (int u = 0; u < NCH; ++u) {
+    if (32 * u < cs) s.colmax[warp * cs + lane + 32 * u] = cm[u];
+  }
+  __syncthreads();
+  for (int j = tid; j < cw; j += NT) {
+    double v = 0;
+    for (int w = 0; w < NW; ++w) v = fmax(v, s.colmax[w * cs + j]);
+    out[cb + j] = v;
+  }
+  __syncthreads();
+}
+
+// One pass over the rows of a row-major matrix: dst[r][j] = f(src[r][j]) with
+//   f(v) = v                       (d == nullptr : the model -> scaled copy)
+//   f(v) = (d_r[r] * v) * d[j]     (a Ruiz scaling step; d_r == nullptr means d_r = d)
+// accumulating |f| into the caller's column partials and (optionally) rowmax.
+// Two rows per warp are in flight so that the loads of the second overlap the first.
+template<int NCH>
+__device__ __forceinline__ void setup_pass(const SetupCtx& s, const double* src, double* dst, int rows, int cb, int cw, const double* d, const double* d_r, double* cm /*regs*/, double* rowmax_out)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < rows; r += NW) {
-    const double* row = M + (size_t)r * s.n;
-    double rm = 0;
+  const int n = s.n;
+  for (int r = warp; r < rows; r += 2 * NW) {
+    const int r2 = r + NW;
+    const bool two = r2 < rows;
+    const double* a0 = src + (size_t)r * n;
+    const double* a1 = src + (size_t)(two ? r2 : r) * n;
+    double v0[NCH], v1[NCH];
 #pragma unroll
-    for (int u = 0; u < SETUP_CH; ++u) {
-      int j = cb + lane + 32 * u;
+    for (int u = 0; u < NCH; ++u) {
+      const int j = cb + lane + 32 * u;
+      const bool in = j < cb + cw;
+      // L2 loads: a neighbouring QP's pass may have left a stale copy of a shared 128-byte line in
+      // this SM's L1 before the upload of this QP's inputs landed (fused feed, see feed_and_setup)
+      v0[u] = in ? __ldcg(a0 + j) : 0.0;
+      v1[u] = (in && two) ? __ldcg(a1 + j) : 0.0;
+    }
+    double dr0 = 1.0, dr1 = 1.0;
+    if (d) {
+      const double* dd = d_r ? d_r : d;
+      dr0 = dd[r];
+      dr1 = two ? dd[r2] : 1.0;
+    }
+    double rm0 = 0, rm1 = 0;
+    double* o0 = dst + (size_t)r * n;
+    double* o1 = dst + (size_t)(two ? r2 : r) * n;
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) {
+      const int j = cb + lane + 32 * u;
       if (j < cb + cw) {
-        double v = fabs(row[j]);
-        cm[u] = fmax(cm[u], v);
-        rm = fmax(rm, v);
+        double w0 = v0[u], w1 = v1[u];
+        if (d) {
+          const double dj = d[j];
+          w0 = dr0 * w0 * dj;
+          w1 = dr1 * w1 * dj;
+        }
+        o0[j] = w0;
+        const double f0 = fabs(w0);
+        cm[u] = fmax(cm[u], f0);
+        rm0 = fmax(rm0, f0);
+        if (two) {
+          o1[j] = w1;
+          const double f1 = fabs(w1);
+          cm[u] = fmax(cm[u], f1);
+          rm1 = fmax(rm1, f1);
+        }
       }
     }
     if (rowmax_out) {
-      rm = warp_max(rm);
-      if (lane == 0) rowmax_out[r] = fmax(rowmax_out[r], rm);
+      rm0 = warp_max(rm0);
+      rm1 = warp_max(rm1);
+      if (lane == 0) {
+        rowmax_out[r] = fmax(rowmax_out[r], rm0);
+        if (two) rowmax_out[r2] = fmax(rowmax_out[r2], rm1);
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(NT) pqp_setup_kernel(PqpSetupArgs A)
+// `sm` : setup_smem_doubles(...) doubles of shared memory; execute: 1 = run Ruiz, 0 = apply the stored delta / c
+template<int NCH>
+__device__ void setup_one_t(const PqpDims& D, const PqpBatchPtrs& P, int q, int execute, int reset_scaling, double* sm)
 {
-  extern __shared__ double sm[];
   __shared__ SetupCtx s;
-  const int q = A.first + blockIdx.x;
-  const int n = A.d.n, ne = A.d.ne, ni = A.d.ni, nc = A.d.nc;
+  const int n = D.n, ne = D.ne, ni = D.ni, nc = D.nc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nd = n + ne + nc;
   const double machine_eps = 2.220446049250313e-16;
+  __syncthreads(); // the previous user of `s` / `sm` is done
   if (tid == 0) {
     s.n = n;
     s.ne = ne;
     s.ni = ni;
     s.nc = nc;
-    s.box = A.d.box;
-    s.hess = A.d.hess;
-    s.Hs = A.p.Hs + (size_t)q * n * n;
-    s.As = A.p.As + (size_t)q * ne * n;
-    s.Cs = A.p.Cs + (size_t)q * ni * n;
-    s.gs = A.p.gs + (size_t)q * n;
-    s.bs = A.p.bs + (size_t)q * ne;
-    s.us = A.p.us + (size_t)q * nc;
-    s.ls = A.p.ls + (size_t)q * nc;
-    s.is = A.p.is + (size_t)q * n;
-    s.delta = A.p.delta + (size_t)q * nd;
+    s.box = D.box;
+    s.hess = D.hess;
+    s.cstride = setup_cstride(n);
+    s.Hs = P.Hs + (size_t)q * n * n;
+    s.As = P.As + (size_t)q * ne * n;
+    s.Cs = P.Cs + (size_t)q * ni * n;
+    s.gs = P.gs + (size_t)q * n;
+    s.bs = P.bs + (size_t)q * ne;
+    s.us = P.us + (size_t)q * nc;
+    s.ls = P.ls + (size_t)q * nc;
+    s.is = P.is + (size_t)q * n;
+    s.delta = P.delta + (size_t)q * nd;
     s.dcur = sm;
     s.colmax = sm + nd;
-    s.rowmax = s.colmax + NW * 256;
-    s.red = s.rowmax + ne + ni;
+    s.rowmax = s.colmax + NW * s.cstride;
+    s.colH = s.rowmax + ne + ni;
+    s.colAC = s.colH + n;
+    s.red = s.colAC + n;
   }
   __syncthreads();
-  const double* Hm = A.p.H + (size_t)q * n * n;
-  const double* Am = A.p.A + (size_t)q * ne * n;
-  const double* Cm = A.p.C + (size_t)q * ni * n;
-  // scaled <- model (helpers.hpp:614-649)
-  if (A.d.hess != PQP_HESSIAN_ZERO) {
-    for (size_t i = tid; i < (size_t)n * n; i += NT) s.Hs[i] = Hm[i];
-  } else {
+  const double* Hm = P.H + (size_t)q * n * n;
+  const double* Am = P.A + (size_t)q * ne * n;
+  const double* Cm = P.C + (size_t)q * ni * n;
+  for (int r = tid; r < ne + ni; r += NT) s.rowmax[r] = 0.0;
+  __syncthreads();
+  // scaled <- model (helpers.hpp:614-649), with the norms of the first Ruiz iteration
+  if (D.hess == PQP_HESSIAN_ZERO) {
     for (size_t i = tid; i < (size_t)n * n; i += NT) s.Hs[i] = 0.0;
   }
-  for (size_t i = tid; i < (size_t)ne * n; i += NT) s.As[i] = Am[i];
-  for (size_t i = tid; i < (size_t)ni * n; i += NT) s.Cs[i] = Cm[i];
-  for (int j = tid; j < n; j += NT) s.gs[j] = A.p.g[(size_t)q * n + j];
-  for (int j = tid; j < ne; j += NT) s.bs[j] = A.p.b[(size_t)q * ne + j];
+  for (int cb = 0; cb < n; cb += 256) {
+    const int cw = min(256, n - cb);
+    double cm[NCH];
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) cm[u] = 0.0;
+    if (D.hess != PQP_HESSIAN_ZERO) {
+      setup_pass<NCH>(s, Hm, s.Hs, n, cb, cw, nullptr, nullptr, cm, nullptr);
+      setup_combine_cols<NCH>(s, cm, cb, cw, s.colH);
+#pragma unroll
+      for (int u = 0; u < NCH; ++u) cm[u] = 0.0;
+    }
+    setup_pass<NCH>(s, Am, s.As, ne, cb, cw, nullptr, nullptr, cm, s.rowmax);
+    setup_pass<NCH>(s, Cm, s.Cs, ni, cb, cw, nullptr, nullptr, cm, s.rowmax + ne);
+    setup_combine_cols<NCH>(s, cm, cb, cw, s.colAC);
+  }
+  for (int j = tid; j < n; j += NT) s.gs[j] = __ldcg(P.g + (size_t)q * n + j);
+  for (int j = tid; j < ne; j += NT) s.bs[j] = __ldcg(P.b + (size_t)q * ne + j);
   for (int j = tid; j < nc; j += NT) {
-    double u = (j < ni) ? A.p.u[(size_t)q * ni + j] : A.p.u_box[(size_t)q * n + j - ni];
-    double l = (j < ni) ? A.p.l[(size_t)q * ni + j] : A.p.l_box[(size_t)q * n + j - ni];
+    double u = (j < ni) ? __ldcg(P.u + (size_t)q * ni + j) : __ldcg(P.u_box + (size_t)q * n + j - ni);
+    double l = (j < ni) ? __ldcg(P.l + (size_t)q * ni + j) : __ldcg(P.l_box + (size_t)q * n + j - ni);
     s.us[j] = u <= 1e20 ? u : 1e20;
     s.ls[j] = l >= -1e20 ? l : -1e20;
   }
@@ -146,19 +256,12 @@ __global__ void __launch_bounds__(NT) pqp_setup_kernel(PqpSetupArgs A)
   // preconditioner is executed and lets it drift on re-application; see
   // DESIGN.md "deliberate deviations")
   for (int j = tid; j < n; j += NT) s.is[j] = 1.0;
-  if (A.reset_scaling || A.execute) {
+  if (reset_scaling || execute) {
     for (int j = tid; j < nd; j += NT) s.delta[j] = 1.0;
-    if (tid == 0) A.p.c[q] = 1.0;
+    if (tid == 0) P.c[q] = 1.0;
   }
   __syncthreads();
 
-  auto scale_AC = [&](const double* d) {
-    for (int r = warp; r < ne + ni; r += NW) {
-      double* row = (r < ne) ? s.As + (size_t)r * n : s.Cs + (size_t)(r - ne) * n;
-      const double dr = d[n + r];
-      for (int j = lane; j < n; j += 32) row[j] = dr * row[j] * d[j];
-    }
-  };
   auto scale_vecs = [&](const double* d) {
     for (int j = tid; j < n; j += NT) s.gs[j] *= d[j];
     for (int j = tid; j < ne; j += NT) s.bs[j] *= d[n + j];
@@ -166,7 +269,7 @@ __global__ void __launch_bounds__(NT) pqp_setup_kernel(PqpSetupArgs A)
       s.us[j] *= d[n + ne + j];
       s.ls[j] *= d[n + ne + j];
     }
-    if (A.d.box) {
+    if (D.box) {
       for (int j = tid; j < n; j += NT) {
         s.is[j] *= d[j];
         s.is[j] *= d[n + ne + ni + j];
@@ -174,19 +277,23 @@ __global__ void __launch_bounds__(NT) pqp_setup_kernel(PqpSetupArgs A)
     }
   };
 
-  if (!A.execute) {
+  if (!execute) {
     // ruiz.hpp:425-511: re-apply the stored scaling
-    const double cq = A.p.c[q];
+    const double cq = P.c[q];
     for (int j = tid; j < nd; j += NT) s.dcur[j] = s.delta[j];
     __syncthreads();
-    scale_AC(s.dcur);
-    if (A.d.hess == PQP_HESSIAN_DENSE) {
+    for (int r = warp; r < ne + ni; r += NW) {
+      double* row = (r < ne) ? s.As + (size_t)r * n : s.Cs + (size_t)(r - ne) * n;
+      const double dr = s.dcur[n + r];
+      for (int j = lane; j < n; j += 32) row[j] = dr * row[j] * s.dcur[j];
+    }
+    if (D.hess == PQP_HESSIAN_DENSE) {
       for (int r = warp; r < n; r += NW) {
         double* row = s.Hs + (size_t)r * n;
         const double dr = s.dcur[r];
         for (int j = lane; j < n; j += 32) row[j] = (dr * row[j] * s.dcur[j]) * cq;
       }
-    } else if (A.d.hess == PQP_HESSIAN_DIAGONAL) {
+    } else if (D.hess == PQP_HESSIAN_DIAGONAL) {
       for (int j = tid; j < n; j += NT) {
         double h = s.Hs[(size_t)j * n + j];
         h *= s.dcur[j];
@@ -197,11 +304,12 @@ __global__ void __launch_bounds__(NT) pqp_setup_kernel(PqpSetupArgs A)
     scale_vecs(s.dcur);
     __syncthreads();
     for (int j = tid; j < n; j += NT) s.gs[j] *= cq;
+    __syncthreads();
     return;
   }
 
   // ruiz.hpp:31-311
-  const PqpQpParams& prm = A.p.params[q];
+  const PqpQpParams& prm = P.params[q];
   const long long max_iter = prm.s.preconditioner_max_iter;
   const double epsilon = prm.s.preconditioner_accuracy;
   const bool for_infeasible = prm.s.primal_infeasibility_solving != 0;
@@ -221,30 +329,14 @@ __global__ void __launch_bounds__(NT) pqp_setup_kernel(PqpSetupArgs A)
     if (!(m > epsilon)) break;
     if (iter == max_iter) break;
     ++iter;
-    // --- norms of the current matrices
-    for (int r = tid; r < ne + ni; r += NT) s.rowmax[r] = 0.0;
-    __syncthreads();
-    for (int cb = 0; cb < n; cb += 256) {
-      const int cw = min(256, n - cb);
-      double cm[SETUP_CH];
-#pragma unroll
-      for (int u = 0; u < SETUP_CH; ++u) cm[u] = 0.0;
-      if (A.d.hess == PQP_HESSIAN_DENSE) setup_norms(s, s.Hs, n, cb, cw, cm, nullptr);
-      setup_norms(s, s.As, ne, cb, cw, cm, s.rowmax);
-      setup_norms(s, s.Cs, ni, cb, cw, cm, s.rowmax + ne);
-#pragma unroll
-      for (int u = 0; u < SETUP_CH; ++u) s.colmax[warp * 256 + lane + 32 * u] = cm[u];
-      __syncthreads();
-      for (int j = tid; j < cw; j += NT) {
-        double v = 0;
-        for (int w = 0; w < NW; ++w) v = fmax(v, s.colmax[w * 256 + j]);
-        const int k = cb + j;
-        if (A.d.hess == PQP_HESSIAN_DIAGONAL) v = fmax(v, fabs(s.Hs[(size_t)k * n + k]));
-        if (A.d.box) v = fmax(v, s.is[k]);
-        const double aux = sqrt(v);
-        s.dcur[k] = (aux == 0.0) ? 1.0 : 1.0 / (aux + machine_eps);
-      }
-      __syncthreads();
+    // --- scaling factors from the norms of the current matrices (ruiz.hpp:68-173)
+    for (int k = tid; k < n; k += NT) {
+      double v = s.colAC[k];
+      if (D.hess == PQP_HESSIAN_DENSE) v = fmax(v, s.colH[k]);
+      if (D.hess == PQP_HESSIAN_DIAGONAL) v = fmax(v, fabs(s.Hs[(size_t)k * n + k]));
+      if (D.box) v = fmax(v, s.is[k]);
+      const double aux = sqrt(v);
+      s.dcur[k] = (aux == 0.0) ? 1.0 : 1.0 / (aux + machine_eps);
     }
     if (for_infeasible) {
       for (int j = tid; j < ne + nc; j += NT) s.dcur[n + j] = 1.0;
@@ -253,53 +345,43 @@ __global__ void __launch_bounds__(NT) pqp_setup_kernel(PqpSetupArgs A)
         const double aux = sqrt(s.rowmax[r]);
         s.dcur[n + r] = (aux == 0.0) ? 1.0 : 1.0 / (aux + machine_eps);
       }
-      if (A.d.box) {
+      if (D.box) {
         for (int k = tid; k < n; k += NT) s.dcur[n + ne + ni + k] = 1.0 / sqrt(s.is[k] + machine_eps);
       }
     }
     __syncthreads();
-    // --- scale
-    scale_AC(s.dcur);
-    scale_vecs(s.dcur);
-    double gamma = 1.0;
-    if (A.d.hess == PQP_HESSIAN_DENSE) {
-      double colsum = 0;
-      for (int cb = 0; cb < n; cb += 256) {
-        const int cw = min(256, n - cb);
-        double cm[SETUP_CH];
+    for (int r = tid; r < ne + ni; r += NT) s.rowmax[r] = 0.0;
+    __syncthreads();
+    // --- scale (ruiz.hpp:175-290); the values written are the next iteration's norms
+    double colsum = 0;
+    for (int cb = 0; cb < n; cb += 256) {
+      const int cw = min(256, n - cb);
+      double cm[NCH];
 #pragma unroll
-        for (int u = 0; u < SETUP_CH; ++u) cm[u] = 0.0;
-        for (int r = warp; r < n; r += NW) {
-          double* row = s.Hs + (size_t)r * n;
-          const double dr = s.dcur[r];
+      for (int u = 0; u < NCH; ++u) cm[u] = 0.0;
+      setup_pass<NCH>(s, s.As, s.As, ne, cb, cw, s.dcur, s.dcur + n, cm, s.rowmax);
+      setup_pass<NCH>(s, s.Cs, s.Cs, ni, cb, cw, s.dcur, s.dcur + n + ne, cm, s.rowmax + ne);
+      setup_combine_cols<NCH>(s, cm, cb, cw, s.colAC);
+      if (D.hess == PQP_HESSIAN_DENSE) {
 #pragma unroll
-          for (int u = 0; u < SETUP_CH; ++u) {
-            int j = cb + lane + 32 * u;
-            if (j < cb + cw) {
-              double v = dr * row[j] * s.dcur[j];
-              row[j] = v;
-              cm[u] = fmax(cm[u], fabs(v));
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < SETUP_CH; ++u) s.colmax[warp * 256 + lane + 32 * u] = cm[u];
-        __syncthreads();
+        for (int u = 0; u < NCH; ++u) cm[u] = 0.0;
+        setup_pass<NCH>(s, s.Hs, s.Hs, n, cb, cw, s.dcur, nullptr, cm, nullptr);
+        setup_combine_cols<NCH>(s, cm, cb, cw, s.colH);
         double part = 0;
-        for (int j = tid; j < cw; j += NT) {
-          double v = 0;
-          for (int w = 0; w < NW; ++w) v = fmax(v, s.colmax[w * 256 + j]);
-          part += v;
-        }
+        for (int j = tid; j < cw; j += NT) part += s.colH[cb + j];
         part = warp_sum(part);
         if (lane == 0) s.red[warp] = part;
         __syncthreads();
         for (int w = 0; w < NW; ++w) colsum += s.red[w];
         __syncthreads();
       }
+    }
+    scale_vecs(s.dcur);
+    double gamma = 1.0;
+    if (D.hess == PQP_HESSIAN_DENSE) {
       gamma = 1.0 / fmax(1.0, colsum / (double)n);
       // quirk 1: H itself is NOT multiplied by gamma here
-    } else if (A.d.hess == PQP_HESSIAN_DIAGONAL) {
+    } else if (D.hess == PQP_HESSIAN_DIAGONAL) {
       double dm = 0;
       for (int j = tid; j < n; j += NT) {
         double h = s.Hs[(size_t)j * n + j];
@@ -323,10 +405,87 @@ __global__ void __launch_bounds__(NT) pqp_setup_kernel(PqpSetupArgs A)
     cacc *= gamma;
     __syncthreads();
   }
-  if (tid == 0) A.p.c[q] = cacc;
+  if (tid == 0) P.c[q] = cacc;
+  __syncthreads();
 }
 
-} // namespace
+// column chunks per lane: n <= 32 -> 1, <= 64 -> 2, <= 128 -> 4, else 8 (blocks of 256 columns)
+__device__ __noinline__ void setup_one(const PqpDims& D, const PqpBatchPtrs& P, int q, int execute, int reset_scaling, double* sm)
+{
+  if (D.n <= 32)
+    setup_one_t<1>(D, P, q, execute, reset_scaling, sm);
+  else if (D.n <= 64)
+    setup_one_t<2>(D, P, q, execute, reset_scaling, sm);
+  else if (D.n <= 128)
+    setup_one_t<4>(D, P, q, execute, reset_scaling, sm);
+  else
+    setup_one_t<8>(D, P, q, execute, reset_scaling, sm);
+}
+
+__global__ void __launch_bounds__(NT) pqp_setup_kernel(const __grid_constant__ PqpSetupArgs A)
+{
+  extern __shared__ __align__(16) double setup_sm[];
+  setup_one(A.d, A.p, A.first + blockIdx.x, A.execute, A.reset_scaling, setup_sm);
+}
+
+// Feed gate + fused set-up of the persistent solve kernels (declared in pqp_device.h terms):
+// a QP is consumed only once the host -> device upload of its inputs has been
+// announced through A.ready[0] (written by a 4-byte copy that follows the
+// chunk's data on the upload stream); then the CTA that owns the QP equilibrates
+// it and goes straight on to the solve. Returns false when the feed was aborted.
+__device__ __noinline__ bool feed_and_setup(const FeedArgs* F, int cur_q, int q, double* sm)
+{
+  const FeedArgs& A = *F;
+  __shared__ int feed_ok;
+  if (A.ready) {
+    if (threadIdx.x == 0) {
+      volatile int32_t* rdy = A.ready;
+      int ok = 1;
+      int need = cur_q + 1 + A.feed_margin;
+      if (need > A.batch) need = A.batch;
+      if (rdy[0] < need) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (rdy[0] < need) {
+          if (rdy[1] != 0) {
+            ok = 0;
+            break;
+          }
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 20000000000ull) { // 20 s without progress: the upload will never come
+            rdy[1] = 1;
+            ok = 0;
+            break;
+          }
+          __nanosleep(200);
+        }
+      }
+      __threadfence();
+      feed_ok = ok;
+    }
+    __syncthreads();
+    const bool ok = feed_ok != 0;
+    __syncthreads();
+    if (!ok) {
+      if (threadIdx.x == 0) A.p.info[(size_t)q * PQP_INFO_DOUBLES + 10] = (double)PQP_NOT_RUN;
+      return false;
+    }
+  }
+#ifndef PQP_EXPERIMENT_EMPTY_SETUP
+  if (A.fused_setup && A.p.params[q].active) setup_one(A.d, A.p, q, (A.fused_setup & 1) ? 1 : 0, (A.fused_setup & 4) ? 1 : 0, sm);
+#endif
+  return true;
+}
+
+} // namespace setupk
+using setupk::pqp_setup_kernel;
+
+extern "C" int64_t
+pqp_setup_smem_bytes(int n, int ne, int ni, int nc)
+{
+  return (int64_t)(sizeof(double) * setupk::setup_smem_doubles(n, ne, ni, nc));
+}
 
 extern "C" int
 pqp_solve_max_smem(void)
@@ -341,8 +500,7 @@ extern "C" int
 pqp_launch_setup(const PqpSetupArgs* a, void* stream)
 {
   if (a->count <= 0) return 0;
-  const int nd = a->d.n + a->d.ne + a->d.nc;
-  size_t smem = sizeof(double) * (size_t)(nd + NW * 256 + a->d.ne + a->d.ni + 64);
+  size_t smem = sizeof(double) * setupk::setup_smem_doubles(a->d.n, a->d.ne, a->d.ni, a->d.nc);
   cudaError_t e = cudaFuncSetAttribute(pqp_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   pqp_setup_kernel<<<a->count, NT, smem, (cudaStream_t)stream>>>(*a);
@@ -356,7 +514,10 @@ pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream)
   // fast kernel: vectors and S^-1 in shared memory; P^-1 either there too or swept inside the S^-1 region
   const int64_t symn = (int64_t)a->d.n * (a->d.n + 1) / 2, symc = (int64_t)a->lay.si_cap * (a->lay.si_cap + 1) / 2;
   const bool fast = a->lay.in_smem[PA_VEC] && a->lay.in_smem[PA_MS] && (a->lay.in_smem[PA_M1] || a->d.hess != PQP_HESSIAN_DENSE || symn <= symc);
-  auto kern = (a->lay.kind == 1) ? tilek::pqp_solve_kernel : (fast ? fastk::pqp_solve_kernel : genk::pqp_solve_kernel);
+  static const bool force_fused = std::getenv("PQP_FORCE_FUSED_KERNEL") != nullptr; // A/B hook: time the <1> instantiation on resident data
+  const bool fused = a->ready != nullptr || a->fused_setup != 0 || force_fused;
+  auto kern = fused ? ((a->lay.kind == 1) ? tilek::pqp_solve_kernel_fused : (fast ? fastk::pqp_solve_kernel_fused : genk::pqp_solve_kernel_fused))
+                    : ((a->lay.kind == 1) ? tilek::pqp_solve_kernel : (fast ? fastk::pqp_solve_kernel : genk::pqp_solve_kernel));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   kern<<<grid, NT, smem, (cudaStream_t)stream>>>(*a);

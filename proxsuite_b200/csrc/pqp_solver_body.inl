@@ -2008,10 +2008,22 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
 
 extern __shared__ __align__(16) double smem_dyn[];
 
-__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArgs A)
+// FUSED: the feed gate + set-up of the end-to-end path are compiled in (a separate instantiation keeps the
+// register allocation of the plain solve kernel untouched)
+template<int FUSED>
+__device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A)
 {
   __shared__ Ctx c;
   __shared__ int cur_q;
+  __shared__ setupk::FeedArgs feed_args;
+  if (FUSED && threadIdx.x == 0) {
+    feed_args.d = A.d;
+    feed_args.p = A.p;
+    feed_args.ready = A.ready;
+    feed_args.batch = A.batch;
+    feed_args.fused_setup = A.fused_setup;
+    feed_args.feed_margin = A.feed_margin;
+  }
   __shared__ long long prof_sh[PH_COUNT];
   const PqpLayout& L = A.lay;
   if (threadIdx.x == 0) {
@@ -2098,9 +2110,13 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArg
   while (true) {
     if (threadIdx.x == 0) cur_q = atomicAdd(A.counter, 1);
     __syncthreads();
-    const int q = A.first + cur_q; // this launch owns the QPs [first, first + batch)
+    const int cq = cur_q;
+    const int q = A.first + cq; // this launch owns the QPs [first, first + batch)
     __syncthreads();
-    if (cur_q >= A.batch) break;
+    if (cq >= A.batch) break;
+    if (FUSED && (A.ready || A.fused_setup)) {
+      if (!setupk::feed_and_setup(&feed_args, cq, q, smem_dyn)) continue;
+    }
     if (!A.p.params[q].active) continue;
     if (threadIdx.x == 0) c.As = As_home;
     __syncthreads();
@@ -2111,3 +2127,13 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArg
   }
 }
 
+// Plain launch: parameters by value, exactly the kernel the device-resident path has always run.
+__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel(PqpSolveArgs A)
+{
+  solve_kernel_body<0>(A);
+}
+// Fused feed: __grid_constant__ lets the non-inlined set-up read the parameters in place.
+__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel_fused(const __grid_constant__ PqpSolveArgs A)
+{
+  solve_kernel_body<1>(A);
+}

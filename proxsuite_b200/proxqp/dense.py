@@ -476,6 +476,17 @@ class DenseBatch:
     def timings(self):
         return self._g.timings()
 
+    def scaled(self, index):
+        """qp.work scaled data and qp.ruiz (delta, c) of QP `index`; test/debug helper."""
+        G = self._g
+        n, ne, ni = G.n, G.n_eq, G.n_in
+        nc = ni + (n if G.box else 0)
+        H = np.zeros((n, n)); g = np.zeros(n); A = np.zeros((ne, n)); b = np.zeros(ne)
+        Cm = np.zeros((ni, n)); u = np.zeros(nc); l = np.zeros(nc); delta = np.zeros(n + ne + nc)
+        c = ct.c_double(0)
+        _capi.check(G.lib.pqp_batch_scaled(G.handle, int(index), _ptr(H), _ptr(g), _ptr(A), _ptr(b), _ptr(Cm), _ptr(u), _ptr(l), _ptr(delta), ct.cast(ct.pointer(c), _VP)))
+        return dict(H=H, g=g, A=A, b=b, C=Cm, u=u, l=l, delta=delta, c=c.value)
+
     def launch_config(self):
         grid, smem, mask, ws = ct.c_int(0), ct.c_int(0), ct.c_int(0), ct.c_int64(0)
         G = self._g

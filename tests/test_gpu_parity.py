@@ -359,11 +359,12 @@ def test_tile_layout_overflow_retry(px, oracle, monkeypatch):
         assert pri <= EPS and dua <= EPS
 
 
-def test_pipelined_init_solve_equals_single_launch(px, monkeypatch):
-    """A large init() uploads in chunks and a solve() issued right after runs one
-    launch per chunk while later chunks are still being copied; the results must
-    be bit-identical to the single persistent launch, and a re-init must not see
-    stale chunk state."""
+@pytest.mark.gpu
+def test_fused_feed_equals_separate_launches(px, monkeypatch):
+    """End-to-end path: a whole-batch init() from host buffers only uploads (in chunks, a progress word behind
+    each) and the solve() issued next runs ONE persistent kernel that waits for each QP's inputs, equilibrates
+    it and solves it. Results must be bit-identical to the separate set-up + solve launches (PQP_E2E=plain) and
+    to the per-chunk launches (PQP_E2E=chunks); a re-init / update of the same object must not see stale state."""
     B, n, ne, ni = 384, 30, 10, 30
     data = [px.dense.random_qp("strongly_convex", i, n, ne, ni) for i in range(B)]
     st = {k: np.stack([d[k] for d in data]) for k in KEYS}
@@ -374,20 +375,68 @@ def test_pipelined_init_solve_equals_single_launch(px, monkeypatch):
             db.settings.eps_abs = EPS
             db.settings.eps_rel = 0
             db.settings.initial_guess = px.InitialGuess.NO_INITIAL_GUESS
+        l0 = db.timings()["kernel_launches"]
         db.init(**st)
         db.solve()
-        return db, db.results()
+        return db, db.results(), db.timings()["kernel_launches"] - l0
 
-    db, r_pipe = run()
-    launches_pipe = db.timings()["kernel_launches"]
-    _, r_pipe2 = run(db)  # same batch object again
-    monkeypatch.setenv("PQP_NO_PIPELINE", "1")
-    db1, r_one = run()
-    assert launches_pipe > db1.timings()["kernel_launches"], "the first run must have used per-chunk launches"
+    db, r_fused, l_fused = run()
+    _, r_fused2, _ = run(db)  # same batch object again
+    # update of the whole batch (new g, b; stored scaling kept) is deferred into the next solve as well
+    g2 = st["g"] * 1.5
+    db.update(g=g2)
+    db.solve()
+    r_upd = db.results()
+    monkeypatch.setenv("PQP_E2E", "plain")
+    db1, r_one, l_one = run()
+    db1.update(g=g2)
+    db1.solve()
+    r_upd1 = db1.results()
+    monkeypatch.setenv("PQP_E2E", "chunks")
+    _, r_chunks, l_chunks = run()
+    assert l_fused == 1 and l_one == 2 and l_chunks > l_one, (l_fused, l_one, l_chunks)
     assert (r_one["info"]["status"] == 0).all()
     for k in ("x", "y", "z"):
-        assert np.array_equal(r_pipe[k], r_one[k]) and np.array_equal(r_pipe2[k], r_one[k])
-    assert np.array_equal(r_pipe["info"]["iter"], r_one["info"]["iter"])
+        assert np.array_equal(r_fused[k], r_one[k]) and np.array_equal(r_fused2[k], r_one[k]) and np.array_equal(r_chunks[k], r_one[k])
+        assert np.array_equal(r_upd[k], r_upd1[k])
+    assert np.array_equal(r_fused["info"]["iter"], r_one["info"]["iter"])
+    assert (r_upd["info"]["status"] == 0).all() and not np.array_equal(r_upd["x"], r_one["x"])
+
+
+@pytest.mark.gpu
+def test_fused_feed_odd_shape_and_scaled_query(px):
+    """Per-QP arrays that are not multiples of a cache line (n = 7), box constraints, and a scaled() query between
+    init() and solve(), which forces the deferred set-up to run as a separate launch."""
+    B, n, ne, ni = 300, 7, 3, 5
+    data = [px.dense.random_qp("box_benchmark", i, n, ne, ni, 0.5) for i in range(B)]
+    keys = list(KEYS) + ["l_box", "u_box"]
+    st = {k: np.stack([d[k] for d in data]) for k in keys}
+
+    def make():
+        db = px.dense.DenseBatch(B, n, ne, ni, True)
+        db.settings.eps_abs = EPS
+        db.settings.eps_rel = 0
+        db.init(**st)
+        return db
+
+    a = make()
+    a.solve()
+    ra = a.results()
+    b = make()
+    sc = b.scaled(5)  # flushes the deferred set-up
+    b.solve()
+    rb = b.results()
+    # seed 125 of this family is primal infeasible (the oracle agrees); everything else is solved
+    assert np.array_equal(ra["info"]["status"], rb["info"]["status"]) and (ra["info"]["status"] == 0).sum() >= B - 2
+    for k in ("x", "y", "z"):
+        assert np.array_equal(ra[k], rb[k])
+    for i in (0, 5, 63, 64, 299):
+        assert ra["info"]["status"][i] == 0
+        pri, dua = kkt_residuals(data[i], ra["x"][i], ra["y"][i], ra["z"][i])
+        assert pri <= EPS and dua <= EPS, (i, pri, dua)
+    D = sc["delta"]
+    assert D.shape[0] == n + ne + ni + n
+    assert np.allclose(sc["A"], D[n:n + ne, None] * data[5]["A"] * D[None, :n], atol=1e-10)
 
 
 def test_tile_kernel_box_constraints(px, oracle):
