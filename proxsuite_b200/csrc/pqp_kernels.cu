@@ -185,6 +185,103 @@ __device__ __forceinline__ void setup_pass(const SetupCtx& s, const double* src,
   }
 }
 
+// The same pass for even n <= 256 (one column block): a lane owns column PAIRS (16-byte L2 loads / stores on
+// pointers known to be global), the scaling vector is read from shared memory as pairs, and the three variants
+// (copy, scale, scale + row norms) are separate instantiations without run-time branches.
+// max of two non-negative finite numbers: one compare + select (fmax adds NaN handling)
+__device__ __forceinline__ double pmax(double a, double b)
+{
+  return b > a ? b : a;
+}
+template<int NP, bool SCALE, bool ROWMAX>
+__device__ __forceinline__ void setup_pass2(const double* src, double* dst, int rows, int n, const double* d, const double* d_r, double2* cm /*regs*/, double* rowmax_out)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int np = n >> 1;
+  const double2* d2 = reinterpret_cast<const double2*>(d);
+  _Pragma("unroll 1") for (int r = warp; r < rows; r += 2 * NW) {
+    const int r2 = r + NW;
+    const bool two = r2 < rows;
+    const double2* a0 = reinterpret_cast<const double2*>(src + (size_t)r * n);
+    const double2* a1 = reinterpret_cast<const double2*>(src + (size_t)(two ? r2 : r) * n);
+    double2 v0[NP], v1[NP];
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+      const int p = lane + 32 * u;
+      const bool in = p < np;
+      v0[u] = in ? __ldcg(a0 + p) : make_double2(0.0, 0.0);
+      v1[u] = (in && two) ? __ldcg(a1 + p) : make_double2(0.0, 0.0);
+    }
+    double dr0 = 1.0, dr1 = 1.0;
+    if (SCALE) {
+      dr0 = d_r[r];
+      dr1 = two ? d_r[r2] : 1.0;
+    }
+    double rm0 = 0, rm1 = 0;
+    double2* o0 = reinterpret_cast<double2*>(dst + (size_t)r * n);
+    double2* o1 = reinterpret_cast<double2*>(dst + (size_t)(two ? r2 : r) * n);
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+      const int p = lane + 32 * u;
+      if (p < np) {
+        double2 w0 = v0[u], w1 = v1[u];
+        if (SCALE) {
+          const double2 dj = d2[p];
+          w0.x = dr0 * w0.x * dj.x;
+          w0.y = dr0 * w0.y * dj.y;
+          w1.x = dr1 * w1.x * dj.x;
+          w1.y = dr1 * w1.y * dj.y;
+        }
+        __stcg(o0 + p, w0);
+        const double f0x = fabs(w0.x), f0y = fabs(w0.y);
+        cm[u].x = pmax(cm[u].x, f0x);
+        cm[u].y = pmax(cm[u].y, f0y);
+        if (ROWMAX) rm0 = pmax(rm0, pmax(f0x, f0y));
+        if (two) {
+          __stcg(o1 + p, w1);
+          const double f1x = fabs(w1.x), f1y = fabs(w1.y);
+          cm[u].x = pmax(cm[u].x, f1x);
+          cm[u].y = pmax(cm[u].y, f1y);
+          if (ROWMAX) rm1 = pmax(rm1, pmax(f1x, f1y));
+        }
+      }
+    }
+    if (ROWMAX) {
+      rm0 = warp_max(rm0);
+      rm1 = warp_max(rm1);
+      if (lane == 0) {
+        rowmax_out[r] = pmax(rowmax_out[r], rm0);
+        if (two) rowmax_out[r2] = pmax(rowmax_out[r2], rm1);
+      }
+    }
+  }
+}
+// per-warp column partials of the pair layout -> out[0 .. n)
+template<int NP>
+__device__ __forceinline__ void setup_combine_cols2(const SetupCtx& s, const double2* cm, int n, double* out)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cs = s.cstride, np = n >> 1;
+  double* const colmax = s.colmax;
+  __builtin_assume(__isShared(colmax));
+  __builtin_assume(__isShared(out));
+#pragma unroll
+  for (int u = 0; u < NP; ++u) {
+    const int p = lane + 32 * u;
+    if (p < np) { // colmax is only 8-byte aligned (it follows n + ne + nc doubles)
+      colmax[warp * cs + 2 * p] = cm[u].x;
+      colmax[warp * cs + 2 * p + 1] = cm[u].y;
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += NT) {
+    double v = 0;
+    for (int w = 0; w < NW; ++w) v = fmax(v, colmax[w * cs + j]);
+    out[j] = v;
+  }
+  __syncthreads();
+}
+
 // `sm` : setup_smem_doubles(...) doubles of shared memory; execute: 1 = run Ruiz, 0 = apply the stored delta / c
 template<int NCH>
 __device__ void setup_one_t(const PqpDims& D, const PqpBatchPtrs& P, int q, int execute, int reset_scaling, double* sm)
@@ -229,6 +326,26 @@ __device__ void setup_one_t(const PqpDims& D, const PqpBatchPtrs& P, int q, int 
   if (D.hess == PQP_HESSIAN_ZERO) {
     for (size_t i = tid; i < (size_t)n * n; i += NT) s.Hs[i] = 0.0;
   }
+  // pair layout: even n, one column block, 16-byte aligned rows (cudaMalloc'ed bases, even row length)
+  constexpr int NP = (NCH + 1) / 2;
+  const bool vec2 = (n % 2 == 0) && n <= 256;
+  double* const gHs = P.Hs + (size_t)q * n * n;
+  double* const gAs = P.As + (size_t)q * ne * n;
+  double* const gCs = P.Cs + (size_t)q * ni * n;
+  if (vec2) {
+    double2 cm2[NP];
+#pragma unroll
+    for (int u = 0; u < NP; ++u) cm2[u] = make_double2(0.0, 0.0);
+    if (D.hess != PQP_HESSIAN_ZERO) {
+      setup_pass2<NP, false, false>(Hm, gHs, n, n, sm, sm, cm2, sm);
+      setup_combine_cols2<NP>(s, cm2, n, s.colH);
+#pragma unroll
+      for (int u = 0; u < NP; ++u) cm2[u] = make_double2(0.0, 0.0);
+    }
+    setup_pass2<NP, false, true>(Am, gAs, ne, n, sm, sm, cm2, s.rowmax);
+    setup_pass2<NP, false, true>(Cm, gCs, ni, n, sm, sm, cm2, s.rowmax + ne);
+    setup_combine_cols2<NP>(s, cm2, n, s.colAC);
+  } else {
   for (int cb = 0; cb < n; cb += 256) {
     const int cw = min(256, n - cb);
     double cm[NCH];
@@ -243,6 +360,7 @@ __device__ void setup_one_t(const PqpDims& D, const PqpBatchPtrs& P, int q, int 
     setup_pass<NCH>(s, Am, s.As, ne, cb, cw, nullptr, nullptr, cm, s.rowmax);
     setup_pass<NCH>(s, Cm, s.Cs, ni, cb, cw, nullptr, nullptr, cm, s.rowmax + ne);
     setup_combine_cols<NCH>(s, cm, cb, cw, s.colAC);
+  }
   }
   for (int j = tid; j < n; j += NT) s.gs[j] = __ldcg(P.g + (size_t)q * n + j);
   for (int j = tid; j < ne; j += NT) s.bs[j] = __ldcg(P.b + (size_t)q * ne + j);
@@ -354,6 +472,27 @@ __device__ void setup_one_t(const PqpDims& D, const PqpBatchPtrs& P, int q, int 
     __syncthreads();
     // --- scale (ruiz.hpp:175-290); the values written are the next iteration's norms
     double colsum = 0;
+    if (vec2) {
+      double2 cm2[NP];
+#pragma unroll
+      for (int u = 0; u < NP; ++u) cm2[u] = make_double2(0.0, 0.0);
+      setup_pass2<NP, true, true>(gAs, gAs, ne, n, s.dcur, s.dcur + n, cm2, s.rowmax);
+      setup_pass2<NP, true, true>(gCs, gCs, ni, n, s.dcur, s.dcur + n + ne, cm2, s.rowmax + ne);
+      setup_combine_cols2<NP>(s, cm2, n, s.colAC);
+      if (D.hess == PQP_HESSIAN_DENSE) {
+#pragma unroll
+        for (int u = 0; u < NP; ++u) cm2[u] = make_double2(0.0, 0.0);
+        setup_pass2<NP, true, false>(gHs, gHs, n, n, s.dcur, s.dcur, cm2, sm);
+        setup_combine_cols2<NP>(s, cm2, n, s.colH);
+        double part = 0;
+        for (int j = tid; j < n; j += NT) part += s.colH[j];
+        part = warp_sum(part);
+        if (lane == 0) s.red[warp] = part;
+        __syncthreads();
+        for (int w = 0; w < NW; ++w) colsum += s.red[w];
+        __syncthreads();
+      }
+    } else
     for (int cb = 0; cb < n; cb += 256) {
       const int cw = min(256, n - cb);
       double cm[NCH];

@@ -479,3 +479,30 @@ def test_maros_meszaros_small_problems(px, oracle):
         qp.settings.initial_guess = px.InitialGuess.WARM_START_WITH_PREVIOUS_RESULT
         qp.solve()
         assert qp.results.info.iter == 0, name
+
+
+@pytest.mark.gpu
+def test_repeated_launches_are_stable(px):
+    """Regression: 300 back-to-back launches of the persistent kernel on the headline batch (bench.py's timed loop).
+    A block-divergence race in the tile kernel's active-set change (thread 0 updated the slot count while late warps
+    still read it) used to end in `illegal instruction` about once per 10^5 QP solves; results must also stay
+    bit-identical from launch to launch."""
+    import torch
+
+    B, n, ne, ni = 1024, 100, 50, 100
+    data = [px.dense.random_qp("strongly_convex", i, n, ne, ni) for i in range(B)]
+    st = {k: np.stack([d[k] for d in data]) for k in KEYS}
+    db = px.dense.DenseBatch(B, n, ne, ni)
+    db.settings.eps_abs = EPS
+    db.settings.eps_rel = 0
+    db.settings.initial_guess = px.InitialGuess.NO_INITIAL_GUESS
+    db.init(**st)
+    db.solve()
+    ref = db.results()["x"].copy()
+    stream = torch.cuda.Stream()
+    for _ in range(30):
+        for _ in range(10):
+            db.solve_async(stream.cuda_stream)
+        torch.cuda.synchronize()
+        db.sync()
+        assert np.array_equal(db.results()["x"], ref)
