@@ -157,7 +157,14 @@ int pqp_batch_settings_set(pqp_batch* b, int64_t index, const pqp_settings* in);
  * QPs; NULL = absent (nullopt). rho/mu_eq/mu_in/manual_eig: NULL = nullopt,
  * else ONE value applied to every addressed QP. Copies the data (the caller's
  * buffers are not retained, helpers.hpp:573-612), clamps the bounds and runs
- * the Ruiz equilibration on the device. */
+ * the Ruiz equilibration on the device.
+ * Asynchrony: pageable host buffers are consumed before the call returns;
+ * PINNED (page-locked) buffers are read by the copy engine after it returns
+ * and must stay unchanged until the next pqp_batch_solve / pqp_batch_sync /
+ * pqp_batch_scaled returns. An init / update of the WHOLE batch only uploads:
+ * the equilibration is done by the solve kernel itself (the CTA that takes a
+ * QP sets it up, then solves it, and starts while later QPs are still being
+ * uploaded); any other call in between runs it as a separate launch first. */
 int pqp_batch_init(pqp_batch* b, int64_t first, int64_t count, const double* H, const double* g, const double* A, const double* b_, const double* C, const double* l, const double* u, const double* l_box, const double* u_box,
                    int compute_preconditioner, const double* rho, const double* mu_eq, const double* mu_in, const double* manual_minimal_H_eigenvalue);
 
