@@ -73,6 +73,7 @@ def lib():
         L.orc_qp_results.argtypes = [C.c_void_p] + [C.c_void_p] * 6
         L.orc_qp_scaled.argtypes = [C.c_void_p] + [C.c_void_p] * 9
         L.orc_qp_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_qp_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double] + [C.c_void_p] * 7
         L.orc_batch_create.restype = C.c_void_p
         L.orc_batch_create.argtypes = [C.c_longlong] * 4 + [C.c_int] * 3
         L.orc_batch_destroy.argtypes = [C.c_void_p]
@@ -223,6 +224,21 @@ class OracleQP:
         out = np.zeros(19)
         lib().orc_qp_counters(self._h, _p(out), int(reset))
         return dict(zip(COUNTER_FIELDS, out))
+
+    def backward(self, loss_derivative, eps=1e-4, rho_new=1e-6, mu_new=1e-6):
+        """dense::compute_backward (dense/compute_ECJ.hpp:29-125) on the solved QP: returns the
+        BackwardData jacobians dL_dH, dL_dg, dL_dA, dL_db, dL_dC, dL_du, dL_dl."""
+        n, ne, ni = self.n, self.n_eq, self.n_in
+        ld = np.ascontiguousarray(np.asarray(loss_derivative, dtype=np.float64))
+        if ld.size != n + ne + ni:
+            raise ValueError("loss_derivative must have dim + n_eq + n_in entries")
+        out = dict(dL_dH=np.zeros((n, n)), dL_dg=np.zeros(n), dL_dA=np.zeros((ne, n)), dL_db=np.zeros(ne),
+                   dL_dC=np.zeros((ni, n)), dL_du=np.zeros(ni), dL_dl=np.zeros(ni))
+        rc = lib().orc_qp_backward(self._h, _p(ld), float(eps), float(rho_new), float(mu_new), *[_p(out[k]) for k in
+                                   ("dL_dH", "dL_dg", "dL_dA", "dL_db", "dL_dC", "dL_du", "dL_dl")])
+        if rc != 0:
+            raise ValueError(lib().orc_last_error().decode())
+        return out
 
 
 class OracleBatch:

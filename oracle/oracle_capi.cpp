@@ -188,6 +188,28 @@ orc_qp_counters(void* p, double* out, int reset)
   if (reset) c = Counters();
 }
 
+// compute_backward (dense/compute_ECJ.hpp:29-125) on a solved QP; any output may be NULL
+int
+orc_qp_backward(void* p, const double* loss_derivative, double eps, double rho_new, double mu_new, double* dL_dH, double* dL_dg, double* dL_dA, double* dL_db, double* dL_dC, double* dL_du, double* dL_dl)
+{
+  try {
+    QP& qp = *static_cast<QP*>(p);
+    BackwardData bd;
+    compute_backward(qp, loss_derivative, bd, eps, rho_new, mu_new);
+    if (dL_dH) std::copy(bd.dL_dH.a.begin(), bd.dL_dH.a.end(), dL_dH);
+    if (dL_dg) std::copy(bd.dL_dg.begin(), bd.dL_dg.end(), dL_dg);
+    if (dL_dA) std::copy(bd.dL_dA.a.begin(), bd.dL_dA.a.end(), dL_dA);
+    if (dL_db) std::copy(bd.dL_db.begin(), bd.dL_db.end(), dL_db);
+    if (dL_dC) std::copy(bd.dL_dC.a.begin(), bd.dL_dC.a.end(), dL_dC);
+    if (dL_du) std::copy(bd.dL_du.begin(), bd.dL_du.end(), dL_du);
+    if (dL_dl) std::copy(bd.dL_dl.begin(), bd.dL_dl.end(), dL_dl);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 long long
 orc_qp_max_nc(void* p)
 {

@@ -969,3 +969,4 @@ struct QP
 } // namespace oracle
 
 #include "proxqp_solver.hpp"
+#include "proxqp_backward.hpp"
