@@ -198,6 +198,21 @@ int pqp_batch_results_device(pqp_batch* b, double** x, double** y, double** z, d
  * QP, for the equilibration identity test. Any pointer may be NULL. */
 int pqp_batch_scaled(pqp_batch* b, int64_t index, double* H, double* g, double* A, double* b_, double* C, double* u, double* l, double* delta, double* c);
 
+/* dense::compute_backward (dense/compute_ECJ.hpp:29-190) for the solved QPs
+ * [first, first+count) == solve_backward_in_parallel (parallel/qp_solve.hpp:84-138):
+ * one more solve of the KKT system regularised with rho_new / mu_new, with the
+ * active set at the solution, then the jacobian-vector products of
+ * BackwardData (backward_data.hpp:27-50). Host pointers, batch-major:
+ * loss_derivative[count][dim + n_eq + n_in] = (dL/dx, dL/dy, dL/dz); outputs
+ * dL_dH[count][dim*dim], dL_dg[count][dim], dL_dA[count][n_eq*dim], dL_db,
+ * dL_dC[count][n_in*dim], dL_du, dL_dl (any may be NULL). Leaves
+ * info.rho = rho_new, info.mu_eq = info.mu_in = mu_new like the reference.
+ * PQP_EINVAL: a QP is dual infeasible (std::invalid_argument in the reference)
+ * or the batch has box constraints (the QP layer has none); PQP_ESTATE: a QP of
+ * the range has not been solved. */
+int pqp_batch_backward(pqp_batch* b, int64_t first, int64_t count, const double* loss_derivative, double eps, double rho_new, double mu_new, double* dL_dH, double* dL_dg, double* dL_dA, double* dL_db, double* dL_dC, double* dL_du,
+                       double* dL_dl);
+
 /* QP<T>::cleanup() (wrapper.hpp:958-962). */
 int pqp_batch_cleanup(pqp_batch* b, int64_t first, int64_t count);
 

@@ -94,6 +94,8 @@ struct pqp_batch
   int32_t* d_ready = nullptr;  // [0] QPs uploaded so far, [1] abort flag
   int32_t* h_ready = nullptr;  // pinned: cumulative QP count behind each upload chunk
   cudaEvent_t ev_feed = nullptr;
+  // QPLayer backward (allocated on first use): loss derivatives in, BackwardData out
+  double *bw_loss = nullptr, *bw_dH = nullptr, *bw_dg = nullptr, *bw_dA = nullptr, *bw_db = nullptr, *bw_dC = nullptr, *bw_du = nullptr, *bw_dl = nullptr;
 };
 
 namespace {
@@ -199,6 +201,9 @@ fill_layout(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, bool want_m1, 
   sz[PA_M1] = (d.hess == PQP_HESSIAN_DENSE) ? rnd((int64_t)n * (n + 1) / 2) : 2; // P^-1, packed with diagonal
   sz[PA_AS] = rnd((int64_t)ne * n);
   sz[PA_MS] = rnd((int64_t)si_cap * (si_cap + 1) / 2 + 2);                       // S^-1, packed with diagonal
+  // build_Pi sweeps P inside the S^-1 region whenever P^-1 itself is not in shared memory: the region must hold
+  // n (n + 1) / 2 doubles as well (fewer constraint rows than variables: cap < n)
+  if (d.hess == PQP_HESSIAN_DENSE) sz[PA_MS] = std::max(sz[PA_MS], rnd((int64_t)n * (n + 1) / 2 + 2));
   sz[PA_G] = rnd((int64_t)cap * (cap + 1) / 2 + 2);
   sz[PA_Y] = 2;
   sz[PA_VEC] = L.vec_doubles;
@@ -1351,6 +1356,95 @@ pqp_batch_scaled(pqp_batch* b, int64_t index, double* H, double* g, double* A, d
   if (int rc = out(l, b->p.ls, nc)) return rc;
   if (int rc = out(delta, b->p.delta, n + ne + nc)) return rc;
   if (int rc = out(c, b->p.c, 1)) return rc;
+  return 0;
+}
+
+int
+pqp_batch_backward(pqp_batch* b, int64_t first, int64_t count, const double* loss_derivative, double eps, double rho_new, double mu_new, double* dL_dH, double* dL_dg, double* dL_dA, double* dL_db, double* dL_dC, double* dL_du, double* dL_dl)
+{
+  if (int rc = check_range(b, first, count)) return rc;
+  if (!loss_derivative) return fail(PQP_EINVAL, "wrong argument size: loss_derivative is required");
+  const PqpDims& d = b->d;
+  if (d.box) return fail(PQP_EINVAL, "compute_backward: QPs with box constraints are not handled by the backward pass");
+  CUDA_TRY(cudaSetDevice(b->device));
+  if (int rc = flush_deferred(b)) return rc;
+  if (b->solve_pending) {
+    if (int rc = pqp_batch_sync(b)) return rc;
+  }
+  for (int64_t i = first; i < first + count; ++i) {
+    if (!b->flags[i].is_initialized || b->hinfo[i].status == PQP_NOT_RUN) return fail(PQP_ESTATE, "compute_backward on a QP that has not been solved");
+    if (b->hinfo[i].status == PQP_DUAL_INFEASIBLE) // compute_ECJ.hpp:37-46
+      return fail(PQP_EINVAL, "the QP problem is not feasible, so computing the derivatives is not valid in this setting. Try enabling infeasible solving if the problem is only primally infeasible.");
+  }
+  if (count == 0) return 0;
+  const size_t B = (size_t)b->B, n = d.n, ne = d.ne, ni = d.ni, nt = n + ne + ni;
+  if (!b->bw_loss) {
+    int rc = 0;
+    rc |= dev_alloc(b, &b->bw_loss, B * nt);
+    rc |= dev_alloc(b, &b->bw_dH, B * n * n);
+    rc |= dev_alloc(b, &b->bw_dg, B * n);
+    rc |= dev_alloc(b, &b->bw_dA, B * ne * n);
+    rc |= dev_alloc(b, &b->bw_db, B * ne);
+    rc |= dev_alloc(b, &b->bw_dC, B * ni * n);
+    rc |= dev_alloc(b, &b->bw_du, B * ni);
+    rc |= dev_alloc(b, &b->bw_dl, B * ni);
+    if (rc != 0) {
+      b->bw_loss = nullptr;
+      return PQP_ECUDA;
+    }
+  }
+  cudaStream_t st = b->stream;
+  CUDA_TRY(cudaMemcpyAsync(b->bw_loss + (size_t)first * nt, loss_derivative, sizeof(double) * (size_t)count * nt, cudaMemcpyHostToDevice, st));
+  std::vector<int32_t> saved((size_t)b->B);
+  for (int64_t i = 0; i < b->B; ++i) {
+    saved[(size_t)i] = b->hparams[i].active;
+    b->hparams[i].active = (i >= first && i < first + count) ? 1 : 0;
+  }
+  cudaError_t e1 = cudaMemcpyAsync(b->p.params, b->hparams.data(), sizeof(PqpQpParams) * (size_t)b->B, cudaMemcpyHostToDevice, st);
+  for (int64_t i = 0; i < b->B; ++i) b->hparams[i].active = saved[(size_t)i];
+  if (e1 != cudaSuccess) return fail(PQP_ECUDA, std::string("cudaMemcpyAsync(params): ") + cudaGetErrorString(e1));
+  CUDA_TRY(cudaMemsetAsync(b->counter, 0, sizeof(int32_t), st));
+  PqpSolveArgs a{};
+  a.d = b->d;
+  a.p = b->p;
+  a.lay = b->lay_gen; // general kernel body, full-capacity layout
+  a.batch = (int32_t)b->B;
+  a.first = 0;
+  a.counter = b->counter;
+  a.ws = b->ws;
+  PqpBackwardArgs k{};
+  k.loss_derivative = b->bw_loss;
+  k.eps = eps;
+  k.rho_new = rho_new;
+  k.mu_new = mu_new;
+  k.dL_dH = b->bw_dH;
+  k.dL_dg = b->bw_dg;
+  k.dL_dA = b->bw_dA;
+  k.dL_db = b->bw_db;
+  k.dL_dC = b->bw_dC;
+  k.dL_du = b->bw_du;
+  k.dL_dl = b->bw_dl;
+  int rc = pqp_launch_backward(&a, &k, b->grid_gen, st);
+  if (rc != 0) return fail(PQP_ECUDA, std::string("backward kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
+  b->launches += 1;
+  auto out = [&](double* dst, const double* src, size_t per) -> int {
+    if (!dst || per == 0) return 0;
+    CUDA_TRY(cudaMemcpyAsync(dst, src + (size_t)first * per, sizeof(double) * (size_t)count * per, cudaMemcpyDeviceToHost, st));
+    return 0;
+  };
+  if (int r = out(dL_dH, b->bw_dH, n * n)) return r;
+  if (int r = out(dL_dg, b->bw_dg, n)) return r;
+  if (int r = out(dL_dA, b->bw_dA, ne * n)) return r;
+  if (int r = out(dL_db, b->bw_db, ne)) return r;
+  if (int r = out(dL_dC, b->bw_dC, ni * n)) return r;
+  if (int r = out(dL_du, b->bw_du, ni)) return r;
+  if (int r = out(dL_dl, b->bw_dl, ni)) return r;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int64_t i = first; i < first + count; ++i) { // compute_ECJ.hpp:66-68
+    b->hinfo[i].rho = rho_new;
+    b->hinfo[i].mu_eq = mu_new;
+    b->hinfo[i].mu_in = mu_new;
+  }
   return 0;
 }
 

@@ -132,6 +132,14 @@ struct PqpSolveArgs
                        // otherwise survive until that SM solves the neighbour)
 };
 
+// QPLayer backward pass (dense/compute_ECJ.hpp:29-190) of the QPs a launch owns: device pointers, batch-major
+struct PqpBackwardArgs
+{
+  const double* loss_derivative; // [B][n + ne + ni] : dL/dx, dL/dy, dL/dz
+  double eps, rho_new, mu_new;
+  double *dL_dH, *dL_dg, *dL_dA, *dL_db, *dL_dC, *dL_du, *dL_dl; // backward_data.hpp:27-50
+};
+
 struct PqpSetupArgs
 {
   PqpDims d;
@@ -147,6 +155,7 @@ extern "C" {
 // host-side launchers implemented in pqp_kernels.cu
 int pqp_launch_setup(const PqpSetupArgs* a, void* stream);
 int pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream);
+int pqp_launch_backward(const PqpSolveArgs* a, const PqpBackwardArgs* k, int grid, void* stream);
 int pqp_solve_max_smem(void);
 int64_t pqp_setup_smem_bytes(int n, int ne, int ni, int nc);
 #ifdef __cplusplus

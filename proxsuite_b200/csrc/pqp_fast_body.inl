@@ -429,7 +429,11 @@ __device__ __noinline__ void bt_dot(const Ctx& c, const double* coef1, const dou
 // constraint rows, which turns every active-set insertion into a gather.
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b)
 {
+#ifdef PQP_CPU_EMU
+  emu::dmma_8x8x4(c0, c1, a, b);
+#else
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+#endif
 }
 __device__ __noinline__ void gemm_tn(const double* __restrict__ CM, int ldc, const double* __restrict__ R, int ldr, int K, int M, int ncols, double* __restrict__ Out, int ldo, bool lower)
 {
@@ -1517,9 +1521,13 @@ __device__ __noinline__ double primal_dual_ls(Ctx& c, const Scal& sc, const pqp_
 
 __device__ __forceinline__ unsigned long long gtimer_ns()
 {
+#ifdef PQP_CPU_EMU
+  return emu::globaltimer();
+#else
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+#endif
 }
 
 __device__ void dbg_write(const PqpSolveArgs& A, int q, int& pos, double a, double b, double c0, double d, double e, double f)
@@ -2096,7 +2104,11 @@ __device__ PQP_SOLVE_ONE_ATTR void solve_one(Ctx& c, const PqpSolveArgs& A, int 
   __syncthreads();
 }
 
+#ifdef PQP_CPU_EMU
+static double* const smem_dyn = emu::dyn_smem;
+#else
 extern __shared__ __align__(16) double smem_dyn[];
+#endif
 
 // FUSED: the feed gate + set-up of the end-to-end path are compiled in (a separate instantiation keeps the
 // register allocation of the plain solve kernel untouched)

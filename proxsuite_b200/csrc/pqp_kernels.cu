@@ -30,6 +30,13 @@
 #define NT PQP_NT
 #define NW PQP_NW
 #define FULL 0xffffffffu
+// tests/emu builds this file with g++ against a functional emulator of the CUDA execution model (cooperative
+// fibers for the threads of a CTA); PQP_CPU_EMU is never defined in the product build
+#ifdef PQP_CPU_EMU
+#define PQP_LAUNCH(kern, grid, block, smem, stream, arg) emu::launch(kern, (int)(grid), (int)(block), (size_t)(smem), arg)
+#else
+#define PQP_LAUNCH(kern, grid, block, smem, stream, arg) kern<<<grid, block, smem, (cudaStream_t)stream>>>(arg)
+#endif
 
 // The solver body is compiled twice: `fastk` assumes that the vector arena and
 // the two inverse blocks are in shared memory (the layout chosen whenever they
@@ -56,9 +63,11 @@ namespace tilek {
 }
 #undef PQP_SM
 #define PQP_SM(p) ((void)0)
+#define PQP_WITH_BACKWARD 1
 namespace genk {
 #include "pqp_solver_body.inl"
 }
+#undef PQP_WITH_BACKWARD
 #undef PQP_SM
 
 namespace setupk {
@@ -563,7 +572,11 @@ __device__ __noinline__ void setup_one(const PqpDims& D, const PqpBatchPtrs& P, 
 
 __global__ void __launch_bounds__(NT) pqp_setup_kernel(const __grid_constant__ PqpSetupArgs A)
 {
+#ifdef PQP_CPU_EMU
+  double* const setup_sm = emu::dyn_smem;
+#else
   extern __shared__ __align__(16) double setup_sm[];
+#endif
   setup_one(A.d, A.p, A.first + blockIdx.x, A.execute, A.reset_scaling, setup_sm);
 }
 
@@ -584,14 +597,22 @@ __device__ __noinline__ bool feed_and_setup(const FeedArgs* F, int cur_q, int q,
       if (need > A.batch) need = A.batch;
       if (rdy[0] < need) {
         unsigned long long t0;
+#ifdef PQP_CPU_EMU
+        t0 = emu::globaltimer();
+#else
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
         while (rdy[0] < need) {
           if (rdy[1] != 0) {
             ok = 0;
             break;
           }
           unsigned long long t1;
+#ifdef PQP_CPU_EMU
+          t1 = emu::globaltimer();
+#else
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+#endif
           if (t1 - t0 > 20000000000ull) { // 20 s without progress: the upload will never come
             rdy[1] = 1;
             ok = 0;
@@ -642,7 +663,22 @@ pqp_launch_setup(const PqpSetupArgs* a, void* stream)
   size_t smem = sizeof(double) * setupk::setup_smem_doubles(a->d.n, a->d.ne, a->d.ni, a->d.nc);
   cudaError_t e = cudaFuncSetAttribute(pqp_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  pqp_setup_kernel<<<a->count, NT, smem, (cudaStream_t)stream>>>(*a);
+  PQP_LAUNCH(pqp_setup_kernel, a->count, NT, smem, stream, *a);
+  return (int)cudaGetLastError();
+}
+
+// the backward pass runs on the general kernel body (any shape, full-capacity layout)
+extern "C" int
+pqp_launch_backward(const PqpSolveArgs* a, const PqpBackwardArgs* k, int grid, void* stream)
+{
+  size_t smem = sizeof(double) * (size_t)a->lay.smem_doubles + (size_t)a->lay.smem_int_bytes;
+  cudaError_t e = cudaFuncSetAttribute(genk::pqp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+#ifdef PQP_CPU_EMU
+  emu::launch2(genk::pqp_backward_kernel, grid, NT, smem, *a, *k);
+#else
+  genk::pqp_backward_kernel<<<grid, NT, smem, (cudaStream_t)stream>>>(*a, *k);
+#endif
   return (int)cudaGetLastError();
 }
 
@@ -659,6 +695,6 @@ pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream)
                     : ((a->lay.kind == 1) ? tilek::pqp_solve_kernel : (fast ? fastk::pqp_solve_kernel : genk::pqp_solve_kernel));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  kern<<<grid, NT, smem, (cudaStream_t)stream>>>(*a);
+  PQP_LAUNCH(kern, grid, NT, smem, stream, *a);
   return (int)cudaGetLastError();
 }

@@ -1443,9 +1443,13 @@ __device__ __noinline__ double primal_dual_ls(Ctx& c, const Scal& sc, const pqp_
 
 __device__ __forceinline__ unsigned long long gtimer_ns()
 {
+#ifdef PQP_CPU_EMU
+  return emu::globaltimer();
+#else
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+#endif
 }
 
 __device__ void dbg_write(const PqpSolveArgs& A, int q, int& pos, double a, double b, double c0, double d, double e, double f)
@@ -2006,17 +2010,166 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
   __syncthreads();
 }
 
-extern __shared__ __align__(16) double smem_dyn[];
+#ifdef PQP_WITH_BACKWARD
+// ---------------------------------------------------------------------------
+// QPLayer backward of one solved QP: dense/compute_ECJ.hpp:29-190
+// (compute_backward, compute_backward_loss_ESG) with backward_data.hpp:27-129.
+// One more solve of the regularised KKT system (rho_new, mu_new) with the
+// active set AT THE SOLUTION, right-hand side = - scaled loss derivative, then
+// the outer products that are the Jacobian-vector products w.r.t. H, g, A, b,
+// C, u, l. Same block elimination as the forward path: P^-1 for rho_new, the
+// dual block for (equalities + active rows) with mu_new, iterative refinement.
+// Deviation (documented in DESIGN.md): a non-zero dL/dz of an ACTIVE row is
+// scaled once by that row's Ruiz factor; the reference rescales the whole
+// block inside its loop over the rows (compute_ECJ.hpp:105-117) — identical
+// for dL/dz = 0, which is what the QP layer passes unless the loss depends on
+// the multipliers.
+// ---------------------------------------------------------------------------
+__device__ void backward_one(Ctx& c, const PqpSolveArgs& A, const PqpBackwardArgs& K, int q)
+{
+  PQP_VECS(c);
+  const PqpQpParams& prm = A.p.params[q];
+  const pqp_settings& S = prm.s;
+  const int n = c.n, ne = c.ne, ni = c.ni, nc = c.nc; // no box constraints on this path: nc == ni
+  const int tid = threadIdx.x;
+  {
+    const PqpBatchPtrs& P = A.p;
+    const double* Asg = P.As + (size_t)q * ne * n;
+    if (tid == 0) {
+      c.Hs = P.Hs + (size_t)q * n * n;
+      c.Cs = P.Cs + (size_t)q * ni * n;
+      c.Hm = P.H + (size_t)q * n * n;
+      c.Am = P.A + (size_t)q * ne * n;
+      c.Cm = P.C + (size_t)q * ni * n;
+      if (!A.lay.in_smem[PA_AS]) c.As = const_cast<double*>(Asg);
+    }
+    __syncthreads();
+    if (A.lay.in_smem[PA_AS]) {
+      _Pragma("unroll 1") for (int i = tid; i < ne * n; i += NT) c.As[i] = Asg[i];
+    }
+    _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) {
+      v_u[j] = P.u[(size_t)q * ni + j];
+      v_l[j] = P.l[(size_t)q * ni + j];
+      c.cons_slot[j] = -1;
+      c.act_up[j] = 0;
+      c.act_low[j] = 0;
+    }
+    _Pragma("unroll 1") for (int j = tid; j < n + ne + nc; j += NT) v_delta[j] = P.delta[(size_t)q * (n + ne + nc) + j];
+    // the solution, in the model's units
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_x[j] = P.x[(size_t)q * n + j];
+    _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_y[j] = P.y[(size_t)q * ne + j];
+    _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) v_z[j] = P.z[(size_t)q * nc + j];
+    _Pragma("unroll 1") for (int j = tid; j < n; j += NT) {
+      v_rx[j] = 0;
+      v_dx[j] = 0;
+    }
+    _Pragma("unroll 1") for (int j = tid; j < c.cap; j += NT) {
+      v_rs[j] = 0;
+      v_ds[j] = 0;
+    }
+    _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) v_dz[j] = 0;
+    if (tid == 0) {
+      c.c_scale = P.c[q];
+      c.ns = 0;
+      c.overflow = 0;
+    }
+    __syncthreads();
+  }
+  const double cs = c.c_scale;
+  const double* dlx = v_delta;
+  const double* dle = v_delta + n;
+  const double* dli = v_delta + n + ne;
 
-// FUSED: the feed gate + set-up of the end-to-end path are compiled in (a separate instantiation keeps the
-// register allocation of the plain solve kernel untouched)
+  Scal sc;
+  sc.rho = K.rho_new; // compute_ECJ.hpp:66-68
+  sc.mu_eq = K.mu_new;
+  sc.mu_in = K.mu_new;
+  sc.mu_eq_inv = 1.0 / sc.mu_eq;
+  sc.mu_in_inv = 1.0 / sc.mu_in;
+  sc.nu = 1.0;
+  sc.iter = 0;
+  sc.iter_ext = 0;
+  sc.mu_updates = 0;
+  sc.status = PQP_SOLVED;
+  sc.iterative_residual = 0;
+  sc.factor_fresh = true;
+
+  // active set at the solution (compute_ECJ.hpp:52-61): C x + z against u and l, unscaled
+  if (ni > 0) mat_pass(c, RowSrc{ c.Cm, nullptr, 0 }, 0, ni, v_x, v_cdx, nullptr, nullptr, nullptr, 1.0);
+  __syncthreads();
+  _Pragma("unroll 1") for (int i = tid; i < ni; i += NT) {
+    const double ctz = v_cdx[i] + v_z[i];
+    c.act_up[i] = (ctz - v_u[i]) >= 0.0;
+    c.act_low[i] = (ctz - v_l[i]) <= 0.0;
+  }
+  __syncthreads();
+  // factorisation from scratch with the new proximal parameters, whole active set inserted (:74-91)
+  build_Pi(c, sc.rho);
+  build_dual_block(c, ne, sc.mu_eq, sc.mu_in);
+  active_set_change(c, sc);
+  sc.factor_fresh = true; // constraints_changed = false: no refactorisation inside the refinement
+  // rhs = - loss derivative, scaled block by block (:93-118)
+  const double* ld = K.loss_derivative + (size_t)q * (n + ne + ni);
+  _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_rx[j] = (-ld[j]) * (dlx[j] * cs);
+  _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_rs[j] = (-ld[n + j]) * dle[j];
+  _Pragma("unroll 1") for (int i = tid; i < ni; i += NT) {
+    const int s = c.cons_slot[i];
+    if (s >= 0) v_rs[s] = (-ld[n + ne + i]) * dli[i];
+  }
+  __syncthreads();
+  iterative_solve(c, sc, S, K.eps);
+  // unpermute, unscale (compute_ECJ.hpp:131-154): dx -> t1, dy -> s1, dz -> dz
+  _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_t1[j] = v_dx[j] * dlx[j];
+  _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) v_s1[j] = v_ds[j] * dle[j] / cs;
+  _Pragma("unroll 1") for (int i = tid; i < ni; i += NT) {
+    const int s = c.cons_slot[i];
+    const double raw = (s >= 0) ? v_ds[s] : ld[n + ne + i];
+    v_dz[i] = raw * dli[i] / cs;
+  }
+  __syncthreads();
+  // jacobian-vector products (compute_ECJ.hpp:156-187), one warp per output row
+  const int lane = tid & 31, warp = tid >> 5;
+  double* oH = K.dL_dH + (size_t)q * n * n;
+  double* oA = K.dL_dA + (size_t)q * ne * n;
+  double* oC = K.dL_dC + (size_t)q * ni * n;
+  _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
+    const double dxi = v_t1[i], xi = v_x[i];
+    _Pragma("unroll 1") for (int j = lane; j < n; j += 32) oH[(size_t)i * n + j] = 0.5 * (dxi * v_x[j] + xi * v_t1[j]);
+  }
+  _Pragma("unroll 1") for (int i = warp; i < ne; i += NW) {
+    const double dyi = v_s1[i], yi = v_y[i];
+    _Pragma("unroll 1") for (int j = lane; j < n; j += 32) oA[(size_t)i * n + j] = dyi * v_x[j] + yi * v_t1[j];
+  }
+  _Pragma("unroll 1") for (int i = warp; i < ni; i += NW) {
+    const double dzi = v_dz[i], zi = v_z[i];
+    _Pragma("unroll 1") for (int j = lane; j < n; j += 32) oC[(size_t)i * n + j] = dzi * v_x[j] + zi * v_t1[j];
+  }
+  _Pragma("unroll 1") for (int j = tid; j < n; j += NT) K.dL_dg[(size_t)q * n + j] = v_t1[j];
+  _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) K.dL_db[(size_t)q * ne + j] = -v_s1[j];
+  _Pragma("unroll 1") for (int i = tid; i < ni; i += NT) {
+    K.dL_du[(size_t)q * ni + i] = c.act_up[i] ? -v_dz[i] : 0.0;
+    K.dL_dl[(size_t)q * ni + i] = c.act_low[i] ? -v_dz[i] : 0.0;
+  }
+  if (tid == 0) A.p.info[(size_t)q * PQP_INFO_DOUBLES + 18] = sc.iterative_residual;
+  __syncthreads();
+}
+#endif // PQP_WITH_BACKWARD
+
+#ifdef PQP_CPU_EMU
+static double* const smem_dyn = emu::dyn_smem;
+#else
+extern __shared__ __align__(16) double smem_dyn[];
+#endif
+
+// FUSED == 1: the feed gate + set-up of the end-to-end path are compiled in (a separate instantiation keeps the
+// register allocation of the plain solve kernel untouched); FUSED == 2: the QPLayer backward pass per QP
 template<int FUSED>
-__device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A)
+__device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A, const PqpBackwardArgs* K = nullptr)
 {
   __shared__ Ctx c;
   __shared__ int cur_q;
   __shared__ setupk::FeedArgs feed_args;
-  if (FUSED && threadIdx.x == 0) {
+  if (FUSED == 1 && threadIdx.x == 0) {
     feed_args.d = A.d;
     feed_args.p = A.p;
     feed_args.ready = A.ready;
@@ -2114,12 +2267,18 @@ __device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A)
     const int q = A.first + cq; // this launch owns the QPs [first, first + batch)
     __syncthreads();
     if (cq >= A.batch) break;
-    if (FUSED && (A.ready || A.fused_setup)) {
+    if (FUSED == 1 && (A.ready || A.fused_setup)) {
       if (!setupk::feed_and_setup(&feed_args, cq, q, smem_dyn)) continue;
     }
     if (!A.p.params[q].active) continue;
     if (threadIdx.x == 0) c.As = As_home;
     __syncthreads();
+#ifdef PQP_WITH_BACKWARD
+    if (FUSED == 2) {
+      backward_one(c, A, *K, q);
+      continue;
+    }
+#endif
     solve_one(c, A, q);
   }
   if (A.prof && threadIdx.x == 0) {
@@ -2137,3 +2296,11 @@ __global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_solve_kernel_fused(const
 {
   solve_kernel_body<1>(A);
 }
+
+#ifdef PQP_WITH_BACKWARD
+// QPLayer backward of every active QP of the launch (same persistent work queue as the solve)
+__global__ void __launch_bounds__(NT, PQP_MIN_CTAS) pqp_backward_kernel(const __grid_constant__ PqpSolveArgs A, const __grid_constant__ PqpBackwardArgs K)
+{
+  solve_kernel_body<2>(A, &K);
+}
+#endif

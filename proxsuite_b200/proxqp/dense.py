@@ -135,12 +135,29 @@ class _Group:
         return dict(setup_ms=a.value, solve_ms=b.value, kernel_launches=n.value)
 
 
+class BackwardData:
+    """dense::BackwardData<T> (dense/backward_data.hpp:27-129, expose-model.hpp:25-41)."""
+
+    def __init__(self, dim=0, n_eq=0, n_in=0):
+        self.initialize(dim, n_eq, n_in)
+
+    def initialize(self, dim, n_eq, n_in):
+        self.dL_dH = np.zeros((dim, dim))
+        self.dL_dg = np.zeros(dim)
+        self.dL_dA = np.zeros((n_eq, dim))
+        self.dL_db = np.zeros(n_eq)
+        self.dL_dC = np.zeros((n_in, dim))
+        self.dL_du = np.zeros(n_in)
+        self.dL_dl = np.zeros(n_in)
+
+
 class _Model:
-    """dense::Model<T> dimensions (dense/model.hpp:23-61)."""
+    """dense::Model<T> dimensions (dense/model.hpp:23-61) and the backward data it owns (model.hpp:45)."""
 
     def __init__(self, dim, n_eq, n_in):
         self.dim, self.n_eq, self.n_in = dim, n_eq, n_in
         self.n_total = dim + n_eq + n_in
+        self.backward_data = BackwardData(dim, n_eq, n_in)
 
 
 class QP:
@@ -355,6 +372,64 @@ def solve_in_parallel(qps, num_threads: Optional[int] = None):
         g.sync()
 
 
+class VectorLossDerivatives(list):
+    """std::vector<dense::Vec<double>> (expose-qpvector.hpp:34-37)."""
+
+
+def _group_backward(group, first, count, loss, eps, rho_backward, mu_backward):
+    n, ne, ni = group.n, group.n_eq, group.n_in
+    loss = np.ascontiguousarray(np.asarray(loss, dtype=np.float64).reshape(count, n + ne + ni))
+    out = dict(dL_dH=np.zeros((count, n, n)), dL_dg=np.zeros((count, n)), dL_dA=np.zeros((count, ne, n)), dL_db=np.zeros((count, ne)),
+               dL_dC=np.zeros((count, ni, n)), dL_du=np.zeros((count, ni)), dL_dl=np.zeros((count, ni)))
+    _capi.check(group.lib.pqp_batch_backward(group.handle, int(first), int(count), _ptr(loss), float(eps), float(rho_backward), float(mu_backward),
+                                             *[_ptr(out[k]) for k in ("dL_dH", "dL_dg", "dL_dA", "dL_db", "dL_dC", "dL_du", "dL_dl")]))
+    return out
+
+
+def _store_backward(qp, out, k):
+    bd = qp.model.backward_data
+    for name in ("dL_dH", "dL_dg", "dL_dA", "dL_db", "dL_dC", "dL_du", "dL_dl"):
+        setattr(bd, name, out[name][k].copy())
+    qp._results.info.rho = float(qp._bw_rho)
+    qp._results.info.mu_eq = qp._results.info.mu_in = float(qp._bw_mu)
+
+
+def compute_backward(qp: QP, loss_derivative, eps: float = 1e-4, rho_backward: float = 1e-6, mu_backward: float = 1e-6):
+    """dense::compute_backward (dense/compute_ECJ.hpp:29-125, expose-backward.hpp:22-30): fills
+    qp.model.backward_data with the derivatives of the loss w.r.t. H, g, A, b, C, u, l."""
+    ld = np.asarray(loss_derivative, dtype=np.float64)
+    if ld.size != qp.model.n_total:
+        raise ValueError("wrong argument size: loss_derivative must have dim + n_eq + n_in entries")
+    qp.results  # pull the latest results / status before the info fields are touched
+    out = _group_backward(qp._group, qp._index, 1, ld, eps, rho_backward, mu_backward)
+    qp._bw_rho, qp._bw_mu = rho_backward, mu_backward
+    _store_backward(qp, out, 0)
+
+
+def solve_backward_in_parallel(num_threads=None, qps=None, loss_derivatives=None, eps: float = 1e-4, rho_backward: float = 1e-6,
+                               mu_backward: float = 1e-6):
+    """dense::solve_backward_in_parallel (parallel/qp_solve.hpp:84-138, expose-parallel.hpp:55-81): the backward pass
+    of every QP of a BatchQP / VectorQP; one kernel launch per run of QPs that are contiguous in a device batch.
+    `num_threads` is accepted for signature parity and ignored."""
+    qps = list(qps)
+    if len(qps) != len(loss_derivatives):
+        raise ValueError("wrong argument size: one loss derivative per QP is required")
+    k = 0
+    while k < len(qps):
+        g, first = qps[k]._group, qps[k]._index
+        e = k
+        while e + 1 < len(qps) and qps[e + 1]._group is g and qps[e + 1]._index == qps[e]._index + 1:
+            e += 1
+        for q in qps[k:e + 1]:
+            q.results
+        loss = np.stack([np.asarray(loss_derivatives[j], dtype=np.float64) for j in range(k, e + 1)])
+        out = _group_backward(g, first, e - k + 1, loss, eps, rho_backward, mu_backward)
+        for j in range(k, e + 1):
+            qps[j]._bw_rho, qps[j]._bw_mu = rho_backward, mu_backward
+            _store_backward(qps[j], out, j - k)
+        k = e + 1
+
+
 def solve(H=None, g=None, A=None, b=None, C=None, l=None, u=None, x=None, y=None, z=None, eps_abs=None, eps_rel=None,
           rho=None, mu_eq=None, mu_in=None, verbose=None, compute_preconditioner=True, compute_timings=False,
           max_iter=None, initial_guess=InitialGuess.EQUALITY_CONSTRAINED_INITIAL_GUESS, check_duality_gap=False,
@@ -475,6 +550,11 @@ class DenseBatch:
 
     def timings(self):
         return self._g.timings()
+
+    def backward(self, loss_derivatives, eps=1e-4, rho_backward=1e-6, mu_backward=1e-6):
+        """solve_backward_in_parallel over the whole batch: loss_derivatives[B, n + n_eq + n_in] -> dict of stacked
+        BackwardData arrays (dL_dH[B, n, n], dL_dg, dL_dA, dL_db, dL_dC, dL_du, dL_dl)."""
+        return _group_backward(self._g, 0, self.batch, loss_derivatives, eps, rho_backward, mu_backward)
 
     def scaled(self, index):
         """qp.work scaled data and qp.ruiz (delta, c) of QP `index`; test/debug helper."""

@@ -1,0 +1,106 @@
+"""GPU tests of the QPLayer backward pass: pqp_batch_backward through the C-ABI and the
+Python mirrors of proxsuite.proxqp.dense.{compute_backward, solve_backward_in_parallel} against the oracle's
+restatement of dense/compute_ECJ.hpp (same seeded QPs, same loss derivatives; tolerance 1e-7 relative on every
+Jacobian) and against the reference's own acceptance test (test/src/dense_backward.cpp: finite differences < 1e-5)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KEYS = "HgAbClu"
+EPS = 1e-9
+BW = ("dL_dH", "dL_dg", "dL_dA", "dL_db", "dL_dC", "dL_du", "dL_dl")
+
+
+@pytest.fixture(scope="module")
+def px():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from proxsuite_b200 import proxqp
+
+    return proxqp
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as O
+
+    O.build()
+    return O
+
+
+@pytest.mark.parametrize("B,n,ne,ni,with_dy", [(16, 10, 5, 0, False), (32, 20, 8, 12, False), (8, 30, 10, 30, True), (4, 12, 3, 2, False)])
+def test_backward_matches_the_oracle(px, oracle, B, n, ne, ni, with_dy):
+    data = [px.dense.random_qp("strongly_convex", 100 + i, n, ne, ni, 0.5, 1e-1) for i in range(B)]
+    db = px.dense.DenseBatch(B, n, ne, ni)
+    db.settings.eps_abs = EPS
+    db.settings.eps_rel = 0
+    db.init(**{k: np.stack([d[k] for d in data]) for k in KEYS})
+    db.solve()
+    assert (db.results()["info"]["status"] == 0).all()
+    rng = np.random.default_rng(B)
+    loss = np.zeros((B, n + ne + ni))
+    loss[:, :n] = rng.standard_normal((B, n))
+    if with_dy:
+        loss[:, n:n + ne] = rng.standard_normal((B, ne))
+    bd = db.backward(loss, 1e-9, 1e-7, 1e-7)
+    for i, d in enumerate(data):
+        q = oracle.OracleQP(n, ne, ni)
+        q.set(eps_abs=EPS, eps_rel=0)
+        q.init(**{k: d[k] for k in KEYS})
+        assert q.solve().info.status == 0
+        bo = q.backward(loss[i], 1e-9, 1e-7, 1e-7)
+        for k in BW:
+            if bo[k].size:
+                assert np.abs(bd[k][i] - bo[k]).max() <= 1e-7 * max(1.0, np.abs(bo[k]).max()), (i, k)
+
+
+def test_backward_against_finite_differences_and_api_mirrors(px):
+    # test/src/dense_backward.cpp:16-86: dx/dg from n backward passes vs central differences of re-solved QPs
+    n, ne, ni = 10, 5, 0
+    d = px.dense.random_qp("strongly_convex", 1, n, ne, ni, 0.85, 1e-1)
+
+    def solved(g):
+        qp = px.dense.QP(n, ne, ni)
+        qp.settings.eps_abs = EPS
+        qp.settings.eps_rel = 0
+        qp.init(d["H"], g, d["A"], d["b"], None, None, None)
+        qp.solve()
+        assert int(qp.results.info.status) == 0
+        return qp
+
+    qp = solved(d["g"])
+    dx_dg = np.zeros((n, n))
+    ld = np.zeros(n + ne + ni)
+    for i in range(n):
+        ld[i] = 1.0
+        px.dense.compute_backward(qp, ld, 1e-5, 1e-7, 1e-7)
+        dx_dg[i] = qp.model.backward_data.dL_dg
+        ld[i] = 0.0
+    assert qp.results.info.rho == 1e-7 and qp.results.info.mu_eq == 1e-7  # compute_ECJ.hpp:66-68
+    fd = np.zeros((n, n))
+    for i in range(n):
+        gp, gm = d["g"].copy(), d["g"].copy()
+        gp[i] += 1e-5
+        gm[i] -= 1e-5
+        fd[:, i] = (solved(gp).results.x - solved(gm).results.x) / 2e-5
+    assert np.abs(fd - dx_dg).max() < 1e-5
+    # batch entry point == single-QP entry point, bitwise
+    batch = px.dense.BatchQP(3)
+    for _ in range(3):
+        q = batch.init_qp_in_place(n, ne, ni)
+        q.settings.eps_abs = EPS
+        q.settings.eps_rel = 0
+        q.init(d["H"], d["g"], d["A"], d["b"], None, None, None)
+    px.dense.solve_in_parallel(batch)
+    losses = px.dense.VectorLossDerivatives()
+    for i in range(3):
+        v = np.zeros(n + ne + ni)
+        v[i] = 1.0
+        losses.append(v)
+    px.dense.solve_backward_in_parallel(None, batch, losses, 1e-5, 1e-7, 1e-7)
+    for i in range(3):
+        assert np.array_equal(batch[i].model.backward_data.dL_dg, dx_dg[i])
+    with pytest.raises(RuntimeError):  # an unsolved QP is refused (PQP_ESTATE)
+        px.dense.compute_backward(px.dense.QP(n, ne, ni), np.zeros(n + ne + ni))
