@@ -155,7 +155,54 @@ def backward_api_case():
     return bool(ok)
 
 
+def qplayer_case():
+    """proxsuite_b200.torch.qplayer.QPFunction (mirror of proxsuite.torch.qplayer): gradients of a loss on the
+    solution w.r.t. every parameter against central finite differences through the layer's own forward pass."""
+    import torch
+
+    from proxsuite_b200.torch import QPFunction
+
+    torch.manual_seed(0)
+    B, n, ne, ni = 2, 5, 2, 4
+    data = [proxqp.dense.random_qp("strongly_convex", 21 + i, n, ne, ni, 0.9, 1e-1) for i in range(B)]
+    assert all(np.abs(d["A"]).sum(1).min() > 0 for d in data)  # no empty equality row (degenerate: no unique gradient)
+    T = {k: torch.tensor(np.stack([d[k] for d in data]), dtype=torch.float64, requires_grad=True) for k in KEYS}
+    layer = QPFunction(eps=1e-10, eps_backward=1e-10, rho_backward=1e-8, mu_backward=1e-8)
+    w = torch.randn(B, n, dtype=torch.float64)
+
+    def loss_of(par):
+        z, lam, nu = layer(par["H"], par["g"], par["A"], par["b"], par["C"], par["l"], par["u"])
+        return (w * z).sum()
+
+    loss = loss_of(T)
+    loss.backward()
+    ok = True
+    worst = {}
+    t = 1e-6
+    rng = np.random.default_rng(1)
+    for k in ("H", "g", "A", "b", "C", "u"):
+        dv = rng.standard_normal(tuple(T[k].shape))
+        if k == "H":
+            dv = 0.5 * (dv + np.swapaxes(dv, 1, 2))
+        dvt = torch.tensor(dv)
+        with torch.no_grad():
+            plus = {kk: (T[kk] + t * dvt if kk == k else T[kk]).detach() for kk in KEYS}
+            minus = {kk: (T[kk] - t * dvt if kk == k else T[kk]).detach() for kk in KEYS}
+            fd = float((loss_of(plus) - loss_of(minus)) / (2 * t))
+        an = float((T[k].grad * dvt).sum())
+        worst[k] = abs(fd - an)
+        ok = ok and abs(fd - an) <= 5e-4 * max(1.0, abs(fd))
+    # a parameter without batch dimension is shared: its gradient is the sum over the batch
+    Hs = torch.tensor(data[0]["H"], dtype=torch.float64, requires_grad=True)
+    z, _, _ = layer(Hs, T["g"].detach(), T["A"].detach(), T["b"].detach(), T["C"].detach(), T["l"].detach(), T["u"].detach())
+    (w * z).sum().backward()
+    ok = ok and tuple(Hs.grad.shape) == (n, n)
+    print(json.dumps(dict(name="qplayer", ok=bool(ok), fd_vs_autograd=worst)), flush=True)
+    return bool(ok)
+
+
 CASES = {
+    "qplayer": qplayer_case,
     "backward_eq": lambda: backward_case("backward_eq", 1, 10, 5, 0, 0.85),
     "backward_mixed": lambda: backward_case("backward_mixed", 3, 8, 3, 6),
     "backward_dy": lambda: backward_case("backward_dy", 5, 8, 3, 6, with_dy=True),

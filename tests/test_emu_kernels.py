@@ -49,3 +49,9 @@ def test_general_layout_with_fewer_constraint_rows_than_variables(emu_lib):
 def test_qplayer_backward_on_the_emulator(emu_lib):
     recs = run_cases(emu_lib, ["backward_eq", "backward_mixed", "backward_dy", "backward_api"])
     assert recs[0]["fd_diff"] < 1e-5 and recs[1]["fd_diff"] < 1e-5  # test/src/dense_backward.cpp acceptance
+
+
+def test_torch_qp_layer_gradients_on_the_emulator(emu_lib):
+    """proxsuite_b200.torch.QPFunction (mirror of proxsuite.torch.qplayer.QPFunction): autograd gradients w.r.t.
+    H, g, A, b, C, u against central finite differences through the layer's forward pass."""
+    run_cases(emu_lib, ["qplayer"])

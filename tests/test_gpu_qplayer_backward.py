@@ -104,3 +104,38 @@ def test_backward_against_finite_differences_and_api_mirrors(px):
         assert np.array_equal(batch[i].model.backward_data.dL_dg, dx_dg[i])
     with pytest.raises(RuntimeError):  # an unsolved QP is refused (PQP_ESTATE)
         px.dense.compute_backward(px.dense.QP(n, ne, ni), np.zeros(n + ne + ni))
+
+
+def test_torch_qp_layer_on_cuda_tensors(px):
+    """proxsuite_b200.torch.QPFunction with CUDA tensors: outputs and gradients live on the device, gradients
+    match central finite differences through the layer (the reference's layer: qplayer.py:93-253)."""
+    import torch
+
+    from proxsuite_b200.torch import QPFunction
+
+    B, n, ne, ni = 4, 12, 4, 8
+    data = [px.dense.random_qp("strongly_convex", 21 + i, n, ne, ni, 0.9, 1e-1) for i in range(B)]
+    T = {k: torch.tensor(np.stack([d[k] for d in data]), dtype=torch.float64, device="cuda", requires_grad=True) for k in KEYS}
+    layer = QPFunction(eps=1e-10, eps_backward=1e-10, rho_backward=1e-8, mu_backward=1e-8)
+    w = torch.randn(B, n, dtype=torch.float64, device="cuda")
+
+    def loss_of(par):
+        z, lam, nu = layer(par["H"], par["g"], par["A"], par["b"], par["C"], par["l"], par["u"])
+        assert z.is_cuda and lam.shape == (B, ne) and nu.shape == (B, ni)
+        return (w * z).sum()
+
+    loss_of(T).backward()
+    rng = np.random.default_rng(1)
+    t = 1e-6
+    for k in ("H", "g", "A", "b", "C", "u"):
+        assert T[k].grad.is_cuda and T[k].grad.shape == T[k].shape
+        dv = rng.standard_normal(tuple(T[k].shape))
+        if k == "H":
+            dv = 0.5 * (dv + np.swapaxes(dv, 1, 2))
+        dvt = torch.tensor(dv, device="cuda")
+        with torch.no_grad():
+            plus = {kk: (T[kk] + t * dvt if kk == k else T[kk]).detach() for kk in KEYS}
+            minus = {kk: (T[kk] - t * dvt if kk == k else T[kk]).detach() for kk in KEYS}
+            fd = float((loss_of(plus) - loss_of(minus)) / (2 * t))
+        an = float((T[k].grad * dvt).sum())
+        assert abs(fd - an) <= 5e-4 * max(1.0, abs(fd)), (k, fd, an)
