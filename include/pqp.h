@@ -193,6 +193,8 @@ int pqp_batch_sync(pqp_batch* b);
  * for QPs [first, first+count); any pointer may be NULL. */
 int pqp_batch_results(pqp_batch* b, int64_t first, int64_t count, double* x, double* y, double* z, double* se, double* si, pqp_info* info);
 int pqp_batch_results_device(pqp_batch* b, double** x, double** y, double** z, double** info20);
+/* x, y, z of the QPs [first, first+count) copied into caller-owned DEVICE buffers (any may be NULL). */
+int pqp_batch_results_copy_device(pqp_batch* b, int64_t first, int64_t count, double* x, double* y, double* z);
 
 /* qp.work scaled model + qp.ruiz (workspace.hpp:35-44, ruiz.hpp:319-320) of one
  * QP, for the equilibration identity test. Any pointer may be NULL. */
@@ -212,6 +214,9 @@ int pqp_batch_scaled(pqp_batch* b, int64_t index, double* H, double* g, double* 
  * the range has not been solved. */
 int pqp_batch_backward(pqp_batch* b, int64_t first, int64_t count, const double* loss_derivative, double eps, double rho_new, double mu_new, double* dL_dH, double* dL_dg, double* dL_dA, double* dL_db, double* dL_dC, double* dL_du,
                        double* dL_dl);
+/* Same with DEVICE pointers for the loss derivatives and the outputs (torch CUDA tensors, no host round trip). */
+int pqp_batch_backward_device(pqp_batch* b, int64_t first, int64_t count, const double* loss_derivative, double eps, double rho_new, double mu_new, double* dL_dH, double* dL_dg, double* dL_dA, double* dL_db, double* dL_dC, double* dL_du,
+                              double* dL_dl);
 
 /* QP<T>::cleanup() (wrapper.hpp:958-962). */
 int pqp_batch_cleanup(pqp_batch* b, int64_t first, int64_t count);

@@ -55,7 +55,7 @@ EXPORTED_SYMBOLS = [
     "pqp_settings_default", "pqp_dense_backend_choice", "pqp_batch_create", "pqp_batch_destroy", "pqp_batch_size",
     "pqp_batch_dims", "pqp_batch_settings_get", "pqp_batch_settings_set", "pqp_batch_init", "pqp_batch_init_device",
     "pqp_batch_update", "pqp_batch_warm_start", "pqp_batch_solve", "pqp_batch_solve_async", "pqp_batch_sync",
-    "pqp_batch_results", "pqp_batch_results_device", "pqp_batch_scaled", "pqp_batch_backward", "pqp_batch_cleanup", "pqp_batch_timings",
+    "pqp_batch_results", "pqp_batch_results_device", "pqp_batch_scaled", "pqp_batch_backward", "pqp_batch_backward_device", "pqp_batch_results_copy_device", "pqp_batch_cleanup", "pqp_batch_timings",
     "pqp_random_qp", "pqp_last_error", "pqp_version",
 ]
 
@@ -100,6 +100,8 @@ def lib():
     L.pqp_batch_scaled.argtypes = [vp, i64] + [vp] * 9
     L.pqp_batch_cleanup.argtypes = [vp, i64, i64]
     L.pqp_batch_backward.argtypes = [vp, i64, i64, vp, dbl, dbl, dbl] + [vp] * 7
+    L.pqp_batch_backward_device.argtypes = [vp, i64, i64, vp, dbl, dbl, dbl] + [vp] * 7
+    L.pqp_batch_results_copy_device.argtypes = [vp, i64, i64, vp, vp, vp]
     L.pqp_batch_timings.argtypes = [vp, vp, vp, vp]
     L.pqp_batch_debug_trace.argtypes = [vp, vp, i64]
     L.pqp_batch_launch_config.argtypes = [vp, vp, vp, vp, vp]

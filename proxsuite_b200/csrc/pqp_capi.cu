@@ -1359,8 +1359,8 @@ pqp_batch_scaled(pqp_batch* b, int64_t index, double* H, double* g, double* A, d
   return 0;
 }
 
-int
-pqp_batch_backward(pqp_batch* b, int64_t first, int64_t count, const double* loss_derivative, double eps, double rho_new, double mu_new, double* dL_dH, double* dL_dg, double* dL_dA, double* dL_db, double* dL_dC, double* dL_du, double* dL_dl)
+static int
+do_backward(pqp_batch* b, int64_t first, int64_t count, const double* loss_derivative, double eps, double rho_new, double mu_new, double* dL_dH, double* dL_dg, double* dL_dA, double* dL_db, double* dL_dC, double* dL_du, double* dL_dl, bool dev_ptrs)
 {
   if (int rc = check_range(b, first, count)) return rc;
   if (!loss_derivative) return fail(PQP_EINVAL, "wrong argument size: loss_derivative is required");
@@ -1394,7 +1394,7 @@ pqp_batch_backward(pqp_batch* b, int64_t first, int64_t count, const double* los
     }
   }
   cudaStream_t st = b->stream;
-  CUDA_TRY(cudaMemcpyAsync(b->bw_loss + (size_t)first * nt, loss_derivative, sizeof(double) * (size_t)count * nt, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b->bw_loss + (size_t)first * nt, loss_derivative, sizeof(double) * (size_t)count * nt, dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   std::vector<int32_t> saved((size_t)b->B);
   for (int64_t i = 0; i < b->B; ++i) {
     saved[(size_t)i] = b->hparams[i].active;
@@ -1429,7 +1429,7 @@ pqp_batch_backward(pqp_batch* b, int64_t first, int64_t count, const double* los
   b->launches += 1;
   auto out = [&](double* dst, const double* src, size_t per) -> int {
     if (!dst || per == 0) return 0;
-    CUDA_TRY(cudaMemcpyAsync(dst, src + (size_t)first * per, sizeof(double) * (size_t)count * per, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(dst, src + (size_t)first * per, sizeof(double) * (size_t)count * per, dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
     return 0;
   };
   if (int r = out(dL_dH, b->bw_dH, n * n)) return r;
@@ -1445,6 +1445,34 @@ pqp_batch_backward(pqp_batch* b, int64_t first, int64_t count, const double* los
     b->hinfo[i].mu_eq = mu_new;
     b->hinfo[i].mu_in = mu_new;
   }
+  return 0;
+}
+
+int
+pqp_batch_backward(pqp_batch* b, int64_t first, int64_t count, const double* loss_derivative, double eps, double rho_new, double mu_new, double* dL_dH, double* dL_dg, double* dL_dA, double* dL_db, double* dL_dC, double* dL_du, double* dL_dl)
+{
+  return do_backward(b, first, count, loss_derivative, eps, rho_new, mu_new, dL_dH, dL_dg, dL_dA, dL_db, dL_dC, dL_du, dL_dl, false);
+}
+int
+pqp_batch_backward_device(pqp_batch* b, int64_t first, int64_t count, const double* loss_derivative, double eps, double rho_new, double mu_new, double* dL_dH, double* dL_dg, double* dL_dA, double* dL_db, double* dL_dC, double* dL_du, double* dL_dl)
+{
+  return do_backward(b, first, count, loss_derivative, eps, rho_new, mu_new, dL_dH, dL_dg, dL_dA, dL_db, dL_dC, dL_du, dL_dl, true);
+}
+
+// x, y, z of the QPs [first, first + count) into caller-owned DEVICE buffers (torch CUDA tensors)
+int
+pqp_batch_results_copy_device(pqp_batch* b, int64_t first, int64_t count, double* x, double* y, double* z)
+{
+  if (int rc = check_range(b, first, count)) return rc;
+  CUDA_TRY(cudaSetDevice(b->device));
+  if (b->solve_pending) {
+    if (int rc = pqp_batch_sync(b)) return rc;
+  }
+  const PqpDims& d = b->d;
+  if (x && count) CUDA_TRY(cudaMemcpyAsync(x, b->p.x + first * d.n, sizeof(double) * (size_t)(count * d.n), cudaMemcpyDeviceToDevice, b->stream));
+  if (y && count && d.ne) CUDA_TRY(cudaMemcpyAsync(y, b->p.y + first * d.ne, sizeof(double) * (size_t)(count * d.ne), cudaMemcpyDeviceToDevice, b->stream));
+  if (z && count && d.nc) CUDA_TRY(cudaMemcpyAsync(z, b->p.z + first * d.nc, sizeof(double) * (size_t)(count * d.nc), cudaMemcpyDeviceToDevice, b->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->stream));
   return 0;
 }
 

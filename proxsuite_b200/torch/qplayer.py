@@ -8,14 +8,19 @@ solve_in_parallel, qplayer.py:105-170), the backward pass is ONE pqp_batch_backw
 primal_infeasibility_solving = False) and the same argument / return order.
 
 Differences: gradients come back in the dtype of the inputs (the reference allocates float32); the closest-feasible
-variant (`structural_feasibility=False`, QPFunctionFn_infeas) is not implemented; tensors cross to the library through
-host memory for now (the C-ABI has device-pointer entry points for the forward pass only)."""
+variant (`structural_feasibility=False`, QPFunctionFn_infeas) is not implemented. CUDA float64 tensors never leave
+the device: the layer hands their data pointers to pqp_batch_init_device / pqp_batch_results_copy_device /
+pqp_batch_backward_device; CPU tensors (and other dtypes) go through the host entry points."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 from torch.autograd import Function
 
+import ctypes as _ct
+import os as _os
+
+from .. import _capi
 from ..proxqp import dense as _dense
 
 
@@ -40,6 +45,21 @@ def _n_batch(*ts):
 
 def _np(t):
     return None if t is None else np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float64)
+
+
+def _on_device(*ts):
+    """Device entry points: every tensor is CUDA (PQP_QPLAYER_DEVICE_API=1 forces them for CPU tensors — only
+    meaningful on the CPU emulator of tests/emu, where "device" memory is host memory)."""
+    ts = [t for t in ts if t is not None]
+    return all(t.is_cuda for t in ts) or _os.environ.get("PQP_QPLAYER_DEVICE_API") == "1"
+
+
+def _dev(t):
+    """contiguous float64 copy (kept alive by the caller) and its data pointer"""
+    if t is None:
+        return None, None
+    c = t.detach().to(torch.float64).contiguous()
+    return c, _ct.c_void_p(c.data_ptr())
 
 
 def QPFunction(eps=1e-9, maxIter=1000, eps_backward=1.0e-4, rho_backward=1.0e-6, mu_backward=1.0e-6, omp_parallel=False,
@@ -70,16 +90,54 @@ def QPFunction(eps=1e-9, maxIter=1000, eps_backward=1.0e-4, rho_backward=1.0e-6,
             s.default_rho = default_rho
             s.refactor_rho_threshold = default_rho  # no refactorization
             s.eps_abs = eps
+            ctx.batch = db
+            ctx.device_api = _on_device(Q, p, A, b, G, l, u)
+            if ctx.device_api:
+                grp = db._g
+                db._push()
+                keep = [_dev(t) for t in (Q, p, A, b, G, l, u)]
+                if Q.is_cuda:  # the library copies on its own stream: the producers of the inputs must be done
+                    torch.cuda.current_stream(Q.device).synchronize()
+                rho = _ct.c_double(default_rho)
+                _capi.check(grp.lib.pqp_batch_init_device(grp.handle, 0, n_batch, *[k[1] for k in keep], None, None, 1,
+                                                         _ct.cast(_ct.pointer(rho), _ct.c_void_p), None, None, None))
+                db.solve()
+                zh = torch.empty((n_batch, nz), dtype=torch.float64, device=Q.device)
+                lam = torch.empty((n_batch, neq), dtype=torch.float64, device=Q.device)
+                nu = torch.empty((n_batch, nineq), dtype=torch.float64, device=Q.device)
+                _capi.check(grp.lib.pqp_batch_results_copy_device(grp.handle, 0, n_batch, _ct.c_void_p(zh.data_ptr()),
+                                                                 _ct.c_void_p(lam.data_ptr()) if neq else None,
+                                                                 _ct.c_void_p(nu.data_ptr()) if nineq else None))
+                return zh.to(Q.dtype), lam.to(Q.dtype), nu.to(Q.dtype)
             db.init(H=_np(Q), g=_np(p), A=_np(A), b=_np(b), C=_np(G), l=_np(l), u=_np(u), rho=default_rho)
             db.solve()
             r = db.results()
-            ctx.batch = db
             mk = lambda a: torch.as_tensor(a, dtype=Q.dtype, device=Q.device)  # noqa: E731
             return mk(r["x"]), mk(r["y"]), mk(r["z"])
 
         @staticmethod
         def backward(ctx, dl_dzhat, dl_dlams, dl_dnus):
             n_batch, dim, neq, nineq = ctx.n_batch, ctx.nz, ctx.neq, ctx.nineq
+            if ctx.device_api:
+                dev, dt = dl_dzhat.device, dl_dzhat.dtype
+                rhs = torch.zeros((n_batch, dim + neq + nineq), dtype=torch.float64, device=dev)  # qplayer.py:197-205
+                rhs[:, :dim] = dl_dzhat
+                if dl_dlams is not None and neq > 0:
+                    rhs[:, dim:dim + neq] = dl_dlams
+                if dl_dnus is not None and nineq > 0:
+                    rhs[:, dim + neq:] = dl_dnus
+                new = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)  # noqa: E731
+                dQ, dp = new(n_batch, dim, dim), new(n_batch, dim)
+                dA, db_ = new(n_batch, neq, dim), new(n_batch, neq)
+                dG, du, dl = new(n_batch, nineq, dim), new(n_batch, nineq), new(n_batch, nineq)
+                ptr = lambda t: _ct.c_void_p(t.data_ptr()) if t.numel() else None  # noqa: E731
+                if rhs.is_cuda:
+                    torch.cuda.current_stream(dev).synchronize()
+                grp = ctx.batch._g
+                _capi.check(grp.lib.pqp_batch_backward_device(grp.handle, 0, n_batch, ptr(rhs), float(eps_backward), float(rho_backward),
+                                                             float(mu_backward), ptr(dQ), ptr(dp), ptr(dA), ptr(db_), ptr(dG), ptr(du), ptr(dl)))
+                return (dQ.to(dt), dp.to(dt), dA.to(dt) if neq else None, db_.to(dt) if neq else None, dG.to(dt) if nineq else None,
+                        dl.to(dt) if nineq else None, du.to(dt) if nineq else None)
             rhs = np.zeros((n_batch, dim + neq + nineq))  # qplayer.py:197-205
             rhs[:, :dim] = _np(dl_dzhat)
             if dl_dlams is not None and neq > 0:

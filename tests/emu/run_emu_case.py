@@ -201,8 +201,18 @@ def qplayer_case():
     return bool(ok)
 
 
+def qplayer_device_api_case():
+    """the same layer through the device-pointer entry points (on the emulator device memory is host memory)"""
+    os.environ["PQP_QPLAYER_DEVICE_API"] = "1"
+    try:
+        return qplayer_case()
+    finally:
+        os.environ.pop("PQP_QPLAYER_DEVICE_API", None)
+
+
 CASES = {
     "qplayer": qplayer_case,
+    "qplayer_device_api": qplayer_device_api_case,
     "backward_eq": lambda: backward_case("backward_eq", 1, 10, 5, 0, 0.85),
     "backward_mixed": lambda: backward_case("backward_mixed", 3, 8, 3, 6),
     "backward_dy": lambda: backward_case("backward_dy", 5, 8, 3, 6, with_dy=True),

@@ -54,4 +54,4 @@ def test_qplayer_backward_on_the_emulator(emu_lib):
 def test_torch_qp_layer_gradients_on_the_emulator(emu_lib):
     """proxsuite_b200.torch.QPFunction (mirror of proxsuite.torch.qplayer.QPFunction): autograd gradients w.r.t.
     H, g, A, b, C, u against central finite differences through the layer's forward pass."""
-    run_cases(emu_lib, ["qplayer"])
+    run_cases(emu_lib, ["qplayer", "qplayer_device_api"])
