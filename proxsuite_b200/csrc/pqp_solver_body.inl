@@ -99,6 +99,7 @@ __device__ __forceinline__ double warp_max(double v)
   return v;
 }
 
+
 // K sums followed by KM maxima reduced over the CTA; the result is returned to
 // every thread (block-uniform control flow depends on it).
 template<int KS, int KM>
@@ -523,10 +524,23 @@ __device__ __noinline__ void sym_sweep_invert(double* __restrict__ T, double* __
       }
       const int ai = i - k0; // position of this row inside the pivot block when 0 <= ai < kb
       const bool inK = (ai >= 0) && (ai < kb);
+      // rows of the pivot block take their panel from the copy every thread holds (a0): their entries (col, i),
+      // i < col, are being overwritten by the thread that owns row col in this very loop
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         const int col = k0 + l;
-        p[l] = (l < kb) ? ((i >= col) ? T[sym_off(i) + col] : T[sym_off(col) + i]) : 0.0;
+        double v = 0.0;
+        if (l < kb) {
+          if (inK) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              if (ai == a) v = a0[a][l];
+            }
+          } else {
+            v = (i >= col) ? T[sym_off(i) + col] : T[sym_off(col) + i];
+          }
+        }
+        p[l] = v;
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {

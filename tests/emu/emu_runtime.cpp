@@ -2,6 +2,20 @@
 #include "emu_shim.h"
 #include <dlfcn.h>
 #include <map>
+// EXPERIMENTAL race detection (`make race`): built with -fsanitize=thread every emulated CUDA thread is a TSan
+// fiber, switches carry NO synchronisation, and the only happens-before edges are the block / warp barriers (release
+// on arrival, acquire on departure, one sync object per barrier generation in flight). Conflicting accesses of two
+// CUDA threads that no barrier separates are then reported with both source lines. It catches such conflicts in
+// small kernels (see the self-test in emu_race_main.cpp) but is NOT reliable on the full solver: TSan keeps only four
+// accesses per 8-byte word, and the round-1 `active_set_change` race, re-introduced on purpose, went unreported.
+// A clean run therefore proves nothing; a report is worth reading.
+#if defined(__SANITIZE_THREAD__)
+#include <sanitizer/tsan_interface.h>
+#define EMU_TSAN 1
+#define EMU_NO_TSAN __attribute__((no_sanitize("thread")))
+#else
+#define EMU_NO_TSAN
+#endif
 #undef threadIdx
 #undef blockIdx
 #undef blockDim
@@ -21,7 +35,10 @@ struct Fiber
   bool done = true;
   void* site = nullptr; // return address of the barrier / collective the fiber waits in
   int kind = 0;         // 1 block barrier, 2 warp barrier, 3 yield
+  void* tsan = nullptr; // TSan fiber context (race-detection build)
+  bool started = false;
 };
+void* sched_tsan = nullptr;
 std::vector<Fiber> fibers;
 ucontext_t sched;
 int cur = -1, nthreads = 0;
@@ -30,6 +47,8 @@ struct Bar
 {
   int count = 0;
   unsigned gen = 0;
+  char token[4] = {}; // TSan sync objects, one per barrier generation in flight (a fast thread arrives at barrier
+                      // g + 1 before a slow one has left g: a single object would leak the later release into it)
 };
 Bar cta_bar;
 Bar warp_bar[64];
@@ -38,45 +57,64 @@ WarpBuf warp_bufs[64];
 unsigned long long ticks = 0;
 int or_acc = 0;
 
+EMU_NO_TSAN void
+to_scheduler()
+{
+#ifdef EMU_TSAN
+  __tsan_switch_to_fiber(sched_tsan, __tsan_switch_to_fiber_no_sync);
+#endif
+  swapcontext(&fibers[(size_t)cur].ctx, &sched);
+}
 void
 trampoline()
 {
   (*body)();
   fibers[(size_t)cur].done = true;
+#ifdef EMU_TSAN
+  __tsan_switch_to_fiber(sched_tsan, 0); // kernel end: everything the thread did happens before the host continues
   swapcontext(&fibers[(size_t)cur].ctx, &sched);
+#else
+  to_scheduler();
+#endif
 }
-void
+EMU_NO_TSAN void
 wait_on(Bar& b, int n)
 {
   const unsigned g = b.gen;
+#ifdef EMU_TSAN
+  __tsan_release(&b.token[g & 3]); // everything this thread did before the barrier ...
+#endif
   if (++b.count == n) {
     b.count = 0;
     ++b.gen;
     ++progress;
   } else {
-    while (b.gen == g) yield();
+    while (b.gen == g) to_scheduler();
   }
+#ifdef EMU_TSAN
+  __tsan_acquire(&b.token[g & 3]); // ... happens before everything any thread does after it
+#endif
 }
 } // namespace
 
-unsigned long long
+EMU_NO_TSAN unsigned long long
 globaltimer()
 {
   return ticks += 1000;
 }
-void
+EMU_NO_TSAN void
 yield()
 {
-  swapcontext(&fibers[(size_t)cur].ctx, &sched);
+  to_scheduler();
 }
-void
+EMU_NO_TSAN void
 block_barrier()
 {
   fibers[(size_t)cur].site = __builtin_return_address(0);
   fibers[(size_t)cur].kind = 1;
   wait_on(cta_bar, nthreads);
 }
-void
+EMU_NO_TSAN void
 warp_barrier()
 {
   const int w = (int)(thread_idx.x >> 5);
@@ -85,15 +123,18 @@ warp_barrier()
   fibers[(size_t)cur].kind = 2;
   wait_on(warp_bar[w], lanes);
 }
-WarpBuf&
+EMU_NO_TSAN WarpBuf&
 warp_buf()
 {
   return warp_bufs[thread_idx.x >> 5];
 }
 
-void
+EMU_NO_TSAN void
 run_grid(int grid, int block, const std::function<void()>& fn)
 {
+#ifdef EMU_TSAN
+  sched_tsan = __tsan_get_current_fiber();
+#endif
   if (block > 2048 || block <= 0) std::abort();
   if ((int)fibers.size() < block) fibers.resize((size_t)block);
   body = &fn;
@@ -113,9 +154,15 @@ run_grid(int grid, int block, const std::function<void()>& fn)
       f.ctx.uc_stack.ss_size = kStack;
       f.ctx.uc_link = &sched;
       f.done = false;
+      f.started = false;
       makecontext(&f.ctx, trampoline, 0);
+#ifdef EMU_TSAN
+      if (f.tsan) __tsan_destroy_fiber(f.tsan);
+      f.tsan = __tsan_create_fiber(0);
+#endif
     }
     int live = block;
+    static const int order_mode = [] { const char* e = std::getenv("EMU_ORDER"); return !e ? 0 : !std::strcmp(e, "reverse") ? 1 : !std::strcmp(e, "stride") ? 2 : 0; }();
     unsigned long long rounds = 0, last_progress = progress, idle_rounds = 0;
     auto stall_report = [&](const char* why) {
       std::fprintf(stderr, "emu: CTA %d stalled (%s); where its threads wait (library offset: threads):\n", b, why);
@@ -134,11 +181,20 @@ run_grid(int grid, int block, const std::function<void()>& fn)
     };
     while (live > 0) {
       live = 0;
-      for (int t = 0; t < block; ++t) {
+      for (int tt = 0; tt < block; ++tt) {
+        // EMU_ORDER=reverse|stride runs the threads of a CTA in another order between barriers: a result that changes
+        // with the order is a data race in the kernel (or a barrier the kernel forgot)
+        const int t = order_mode == 1 ? block - 1 - tt : order_mode == 2 ? (int)(((long long)tt * 37 + 11) % block) : tt;
         Fiber& f = fibers[(size_t)t];
         if (f.done) continue;
         cur = t;
         thread_idx = Idx{ (unsigned)t, 0, 0 };
+#ifdef EMU_TSAN
+        // the launch orders the host's writes before the thread's first instruction; later switches carry no
+        // synchronisation (only barriers order CUDA threads)
+        __tsan_switch_to_fiber(f.tsan, f.started ? __tsan_switch_to_fiber_no_sync : 0);
+        f.started = true;
+#endif
         swapcontext(&sched, &f.ctx);
         if (!f.done) ++live;
       }
@@ -159,7 +215,7 @@ run_grid(int grid, int block, const std::function<void()>& fn)
 }
 } // namespace emu
 
-int
+EMU_NO_TSAN int
 __syncthreads_or(int p)
 {
   // all threads contribute, then all read, then the accumulator is cleared

@@ -175,16 +175,7 @@ template<class T>
 static inline T
 atomicAdd(T* p, T v)
 {
-  T old = *p;
-  *p = old + v;
-  return old;
-}
-static inline int
-atomicAdd(int* p, int v)
-{
-  int old = *p;
-  *p = old + v;
-  return old;
+  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 static inline long long
 clock64()

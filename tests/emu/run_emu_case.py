@@ -201,6 +201,35 @@ def qplayer_case():
     return bool(ok)
 
 
+def closest_feasible_case():
+    """primal_infeasibility_solving (closest feasible QP, solver.hpp:1572-1595, utils.hpp:241-248): the reference's
+    infeasible QP (test/src/dense_qp_eq.cpp:217-258) and a random QP with an inconsistent pair of equality rows; same
+    status, x and slacks as the oracle (the multipliers of an infeasible QP diverge with the iteration count)."""
+    ok = True
+    H = 2 * np.eye(2); g = np.array([-18.0, -12.0]); C = np.array([[1.0, 0.0], [0.0, 1.0], [-1.0, 0.0]])
+    l = np.full(3, -1e20); u = np.array([10.0, 10.0, -20.0])
+    n, ne, ni = 8, 4, 5
+    d = proxqp.dense.random_qp("strongly_convex", 7, n, ne, ni, 0.6, 1e-1)
+    A = d["A"].copy(); b = d["b"].copy()
+    A[3] = A[0]; b[3] = b[0] + 1.0
+    for (dims, kw) in (((2, 0, 3), dict(H=H, g=g, C=C, l=l, u=u)), ((n, ne, ni), dict(H=d["H"], g=d["g"], A=A, b=b, C=d["C"], l=d["l"], u=d["u"]))):
+        qp = proxqp.dense.QP(*dims)
+        qp.settings.eps_abs = EPS
+        qp.settings.eps_rel = 0
+        qp.settings.primal_infeasibility_solving = True
+        qp.init(kw["H"], kw["g"], kw.get("A"), kw.get("b"), kw["C"], kw["l"], kw["u"])
+        qp.solve()
+        r = qp.results
+        o = O.OracleQP(*dims)
+        o.set(eps_abs=EPS, eps_rel=0, primal_infeasibility_solving=1)
+        o.init(**kw)
+        ro = o.solve()
+        ok = ok and int(r.info.status) == ro.info.status and np.abs(r.x - ro.x).max() <= 1e-6 * max(1.0, np.abs(ro.x).max())
+        ok = ok and np.abs(r.si - ro.si).max() <= 1e-6 and (dims[1] == 0 or np.abs(r.se - ro.se).max() <= 1e-6)
+    print(json.dumps(dict(name="closest_feasible", ok=bool(ok))), flush=True)
+    return bool(ok)
+
+
 def qplayer_device_api_case():
     """the same layer through the device-pointer entry points (on the emulator device memory is host memory)"""
     os.environ["PQP_QPLAYER_DEVICE_API"] = "1"
@@ -213,6 +242,7 @@ def qplayer_device_api_case():
 CASES = {
     "qplayer": qplayer_case,
     "qplayer_device_api": qplayer_device_api_case,
+    "closest_feasible": closest_feasible_case,
     "backward_eq": lambda: backward_case("backward_eq", 1, 10, 5, 0, 0.85),
     "backward_mixed": lambda: backward_case("backward_mixed", 3, 8, 3, 6),
     "backward_dy": lambda: backward_case("backward_dy", 5, 8, 3, 6, with_dy=True),

@@ -24,8 +24,11 @@ def emu_lib():
     return lib
 
 
-def run_cases(lib, names):
+def run_cases(lib, names, order=None):
     env = dict(os.environ, PQP_B200_LIB=lib)
+    env.pop("EMU_ORDER", None)
+    if order:
+        env["EMU_ORDER"] = order
     env.pop("PQP_LAYOUT", None)
     env.pop("PQP_E2E", None)
     p = subprocess.run([sys.executable, os.path.join(EMU, "run_emu_case.py")] + names, env=env, capture_output=True, text=True, timeout=900)
@@ -37,7 +40,7 @@ def run_cases(lib, names):
 
 def test_forward_parity_of_every_kernel_variant_on_the_emulator(emu_lib):
     run_cases(emu_lib, ["tile_small", "tile_plain_setup", "tile_eq_guess", "tile_box", "general_odd", "general_diag",
-                        "generic_layout", "no_inequalities", "degenerate", "not_strongly_convex"])
+                        "generic_layout", "no_inequalities", "degenerate", "not_strongly_convex", "closest_feasible"])
 
 
 def test_general_layout_with_fewer_constraint_rows_than_variables(emu_lib):
@@ -55,3 +58,13 @@ def test_torch_qp_layer_gradients_on_the_emulator(emu_lib):
     """proxsuite_b200.torch.QPFunction (mirror of proxsuite.torch.qplayer.QPFunction): autograd gradients w.r.t.
     H, g, A, b, C, u against central finite differences through the layer's forward pass."""
     run_cases(emu_lib, ["qplayer", "qplayer_device_api"])
+
+
+@pytest.mark.parametrize("order", ["reverse", "stride"])
+def test_results_do_not_depend_on_the_thread_order_between_barriers(emu_lib, order):
+    """Order fuzzing: the emulator runs the threads of a CTA in a different order between barriers (EMU_ORDER). A
+    kernel whose result changes with that order has a data race or relies on warp lockstep without saying so. Found
+    this way: the pivot-block rows of the general kernel's sweep inversion re-read panel entries that a sibling
+    thread of the same warp was overwriting (harmless under lockstep, wrong under any other order)."""
+    run_cases(emu_lib, ["tile_small", "tile_box", "general_odd", "general_diag", "generic_layout", "few_rows_generic",
+                        "backward_mixed"], order=order)
