@@ -1077,6 +1077,9 @@ __device__ void refactorize(Ctx& c, Scal& sc)
   sc.factor_fresh = true;
 }
 
+#ifndef PQP_TIGHT_REFINE
+#define PQP_TIGHT_REFINE 1e-10
+#endif
 // solver.hpp:408-541
 __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_settings& S, double eps)
 {
@@ -1091,7 +1094,14 @@ __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_setting
     PROF_ADD(PH_RESID, tp);
     ++it;
     double prev = err;
-    while (err >= eps) {
+    // Diagonal / zero Hessians: P^-1 = diag(1 / (H_ii + rho)) reaches 1 / rho where H_ii = 0, the Schur complement
+    // is then badly conditioned and the explicit S^-1 carries ~1e-8 relative error. The reference's LDL^T does not
+    // have that loss, so its first solve is already accurate; here the refinement (one solve + one residual per
+    // round, error shrinking ~1e-8 per round) is driven down to PQP_TIGHT_REFINE instead of stopping at the inner
+    // tolerance, which keeps the Newton steps as good as the reference's (3-6x fewer Newton iterations on the
+    // diagonal-Hessian benchmark family, measured on the emulator).
+    const double eps_ref = (c.hess != PQP_HESSIAN_DENSE) ? fmin(eps, PQP_TIGHT_REFINE) : eps;
+    while (err >= eps_ref) {
       if (it >= S.nb_iterative_refinement) break;
       ++it;
       tp = PROF_T0();
