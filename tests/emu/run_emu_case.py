@@ -254,6 +254,7 @@ CASES = {
     "general_odd": lambda: case("general_odd", "strongly_convex", 2, 7, 3, 5),
     "general_diag": lambda: case("general_diag", "diagonal_benchmark", 2, 9, 3, 4, box=True, hessian=proxqp.HessianType.Diagonal, sparsity=0.5),
     "generic_layout": lambda: case("generic_layout", "strongly_convex", 2, 12, 4, 8, layout="generic"),
+    "gated_feed": lambda: case("gated_feed", "strongly_convex", 260, 6, 2, 4),  # >= 256 QPs from host buffers: chunked upload + progress word + feed margin
     "few_rows_generic": lambda: case("few_rows_generic", "strongly_convex", 2, 8, 3, 2, layout="generic"),
     "no_inequalities": lambda: case("no_inequalities", "strongly_convex", 2, 10, 5, 0),
     "degenerate": lambda: case("degenerate", "degenerate", 2, 10, 3, 4),
