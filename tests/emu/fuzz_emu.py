@@ -55,6 +55,13 @@ for case in range(N):
         db.init(**{k: np.stack([d[k] for d in data]) for k in keys})
         db.solve()
         r = db.results()
+        do_bw = (not box) and hess == 1 and bool((r["info"]["status"] == 0).all())
+        if do_bw:
+            loss = np.zeros((B, n + ne + ni))
+            loss[:, :n] = rng.standard_normal((B, n))
+            if ne and rng.random() < 0.5:
+                loss[:, n:n + ne] = rng.standard_normal((B, ne))
+            bd = db.backward(loss, 1e-9, 1e-7, 1e-7)
         for i, d in enumerate(data):
             q = O.OracleQP(n, ne, ni, box_constraints=box, hessian_type=hess)
             q.set(eps_abs=EPS, eps_rel=0, initial_guess=ig, max_iter=200)
@@ -67,6 +74,12 @@ for case in range(N):
                 ok = pri <= EPS and dua <= EPS
                 if hess == 1:  # strictly convex: the solution is unique
                     ok = ok and np.abs(r["x"][i] - ro.x).max() <= 1e-6 * max(1.0, np.abs(ro.x).max())
+            if ok and do_bw:
+                bo = q.backward(loss[i], 1e-9, 1e-7, 1e-7)
+                for k in bo:
+                    if bo[k].size and np.abs(bd[k][i] - bo[k]).max() > 1e-6 * max(1.0, np.abs(bo[k]).max()):
+                        ok = False
+                        desc["backward_key"] = k
             if not ok:
                 bad += 1
                 print("MISMATCH", json.dumps(desc), "qp", i, "status", st, ro.info.status, "iter", int(r["info"]["iter"][i]), ro.info.iter, flush=True)
