@@ -5,13 +5,14 @@
     python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the reference's
                                                               algorithm on the host cores)
 
-Workload (BASELINE.json configs[1]): per GPU a BatchQP of 1024 random dense QPs,
+Workload (the shape BASELINE.json's metric and the north-star target are quoted on: configs[1]'s QP shape at the
+headline batch of 4096): per GPU a BatchQP of 4096 random dense QPs,
 n=100, n_eq=50, n_in=100, fp64, generated exactly like the reference's batch
 benchmark (benchmark/timings-parallel.cpp:19-54: set_seed(i) +
 dense_strongly_convex_qp(sparsity 0.15, strong convexity 1e-2), eps_abs=1e-9,
 eps_rel=0, NO_INITIAL_GUESS). A "step" is one solve_in_parallel over the whole
 (already init-ed) batch — what timings-parallel.cpp:208-232 times. Weak scaling:
-every rank owns its own 1024 QPs, no collective in the data path.
+every rank owns its own 4096 QPs (--batch 1024 gives configs[1]'s literal batch), no collective in the data path.
 
 `value`   : QPs/s with inputs resident in HBM, CUDA-event timed on the launching stream.
 `e2e`     : QPs/s through the public API with HOST (pinned) inputs, every step: init (chunked H2D
@@ -39,7 +40,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_DIM, N_EQ, N_IN = 100, 50, 100
-BATCH_PER_GPU = 1024
+BATCH_PER_GPU = 4096  # headline batch (north_star: 4096 QPs on 1 GPU); configs[1]'s literal batch is --batch 1024
+CPU_SAMPLE = 1024     # QPs per CPU-arm step (a bounded sample of the same workload: seeds 0..1023)
 SPARSITY, STRONG_CONVEXITY = 0.15, 1e-2
 EPS_ABS = 1e-9
 KEYS = "HgAbClu"
@@ -126,81 +128,101 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def best_thread_count(batch, candidates):
-    """The CPU arm gets the thread count that serves it best on this host: every logical CPU, or
-    half of them (the reference's own default, parallel/qp_solve.hpp:45-49; SMT siblings can hurt)."""
-    best_t, best_time = None, None
-    for t in candidates:
-        batch.solve(t)  # page-in / thread start
-        dt = batch.solve(t)
-        if best_time is None or dt < best_time:
-            best_t, best_time = t, dt
-    return best_t
+def pin_openmp_env(threads):
+    """OpenMP environment of the CPU arm, set BEFORE libgomp is loaded (it reads the environment once): one thread per
+    logical CPU, no migration, spinning workers. torchrun / the driver may export OMP_NUM_THREADS=1; the CPU arm must not
+    inherit that."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ["OMP_PROC_BIND"] = "true"
+    os.environ["OMP_PLACES"] = "threads"
+    os.environ["OMP_WAIT_POLICY"] = "active"
+    os.environ["OMP_DYNAMIC"] = "false"
+    os.environ.pop("OMP_THREAD_LIMIT", None)
 
 
-def cpu_baseline(sample, reps, threads=0):
-    """The oracle (C++ restatement of the reference, kind "port") on the host
-    cores: OpenMP schedule(dynamic) over QPs with all threads, batch already
-    init-ed (benchmark/timings-parallel.cpp:208-232)."""
+def make_oracle_batch(sample):
+    """`sample` QPs of the workload (seeds 0..sample-1) set up in the oracle (C++ restatement of the reference, kind
+    "port", rebuilt with -march=native on this machine), ready for solve_in_parallel."""
     from oracle import oracle as O
 
-    O.build()
+    flags = O.use_native()
     st = generate(0, sample, O.generate_qp)
     b = O.OracleBatch(sample, N_DIM, N_EQ, N_IN)
     for i in range(sample):
         q = b[i]
         q.set(eps_abs=EPS_ABS, eps_rel=0, initial_guess=O.NO_INITIAL_GUESS)
         q.init(**{k: st[k][i] for k in KEYS})
+    return b, flags
+
+
+def best_thread_count(batch, candidates):
+    """The CPU arm gets the thread count that serves it best on this host: every logical CPU, or
+    half of them (the reference's own default, parallel/qp_solve.hpp:45-49; SMT siblings can hurt).
+    Best of three solves per candidate, after one untimed solve (page-in, thread start, clock ramp)."""
+    best_t, best_time, tried = None, None, {}
+    for t in candidates:
+        batch.solve(t)
+        dt = min(batch.solve(t) for _ in range(3))
+        tried[t] = dt
+        if best_time is None or dt < best_time:
+            best_t, best_time = t, dt
+    return best_t, tried
+
+
+def cpu_baseline(sample, reps, threads=0):
+    """The oracle on the host cores: OpenMP schedule(dynamic) over QPs with all threads, batch already
+    init-ed (benchmark/timings-parallel.cpp:208-232)."""
+    b, flags = make_oracle_batch(sample)
     H = host_threads()
-    T = threads or best_thread_count(b, sorted({H, max(1, H // 2)}, reverse=True))
+    tried = {}
+    if threads:
+        T = threads
+    else:
+        T, tried = best_thread_count(b, sorted({H, max(1, H // 2)}, reverse=True))
     b.solve(T)  # warm-up
     b.counters(reset=True)
-    best = None
-    tot = 0.0
-    for _ in range(reps):
-        t = b.solve(T)
-        tot += t
-        best = t if best is None else min(best, t)
+    times = [b.solve(T) for _ in range(reps)]
     cnt = b.counters()
     cnt = {k: v / reps for k, v in cnt.items()}
     solved = sum(1 for i in range(sample) if b[i].results().info.status == 0)
-    return dict(qps=sample / best, best_s=best, total_s=tot, cores=T, sample=sample, reps=reps, solved=solved, counters=cnt)
+    return dict(qps=sample / min(times), best_s=min(times), total_s=sum(times), times=times, cores=T, host_threads=H, tried=tried, sample=sample,
+                reps=reps, solved=solved, counters=cnt, flags=flags)
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path. The reference itself cannot be
     compiled here (Eigen 3 absent), so this is the oracle
-    port with every host thread; rank 0 alone runs."""
+    port (rebuilt with -march=native on this machine) with every host thread; rank 0 alone runs.
+    Each step = solve_in_parallel over a CPU_SAMPLE-QP sample of the workload; `value` = QPs of the K timed
+    steps / their total time. Per-step times, the thread count tried / chosen and the load average are printed
+    so that an outlier run can be recognised (`steps_ms`, `threads_tried_ms`, `loadavg`)."""
     if rank != 0:
         return
-    sample = 1024  # the whole per-GPU batch of the GPU arm
-    from oracle import oracle as O
-
-    O.build()
-    st = generate(0, sample, O.generate_qp)
-    b = O.OracleBatch(sample, N_DIM, N_EQ, N_IN)
-    for i in range(sample):
-        q = b[i]
-        q.set(eps_abs=EPS_ABS, eps_rel=0, initial_guess=O.NO_INITIAL_GUESS)
-        q.init(**{k: st[k][i] for k in KEYS})
+    sample = CPU_SAMPLE
     H = host_threads()
-    T = best_thread_count(b, sorted({H, max(1, H // 2)}, reverse=True))
-    for _ in range(args.warmup):
+    pin_openmp_env(H)
+    b, flags = make_oracle_batch(sample)
+    T, tried = best_thread_count(b, sorted({H, max(1, H // 2)}, reverse=True))
+    for _ in range(max(args.warmup, 3)):
         b.solve(T)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        b.solve(T)
-    dt = time.perf_counter() - t0
+    times = [b.solve(T) for _ in range(args.steps)]  # orc_batch_solve returns the wall time of the parallel region
+    dt = sum(times)
     qps = sample * args.steps / dt
+    try:
+        load = os.getloadavg()[0]
+    except OSError:
+        load = None
     line = {
         "impl": "reference", "metric": "QPs solved/sec (batch dense, n=100)", "value": qps, "unit": "QPs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BatchQP dense n={N_DIM} n_eq={N_EQ} n_in={N_IN} eps_abs=1e-9 NO_INITIAL_GUESS; step = solve_in_parallel over a {sample}-QP sample of the 1024-QP batch, OpenMP schedule(dynamic)",
-                   "batch_per_step": sample},
+        "config": {"workload": f"BatchQP dense n={N_DIM} n_eq={N_EQ} n_in={N_IN} eps_abs=1e-9 NO_INITIAL_GUESS; step = solve_in_parallel over a {sample}-QP sample (seeds 0..{sample - 1}) of the {BATCH_PER_GPU}-QP batch, OpenMP schedule(dynamic)",
+                   "batch_per_step": sample, "compiler_flags": flags},
         "cpu_baseline": {"value": qps, "unit": "QPs/s", "cores": T, "kind": "port", "sample": f"{sample} QPs x {args.steps} steps, seeds 0..{sample - 1}"},
         "e2e": {"value": qps, "unit": "QPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "steps_ms": [round(1e3 * t, 2) for t in times], "best_step_qps": sample / min(times), "host_threads": H,
+        "threads_tried_ms": {str(k): round(1e3 * v, 2) for k, v in tried.items()}, "loadavg": load,
     }
     print(json.dumps(line))
 
@@ -211,7 +233,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="QPs per GPU (BASELINE.json configs[1]: 1024)")
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="QPs per GPU (default 4096, the north-star batch; BASELINE.json configs[1] literally: 1024)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -293,15 +315,15 @@ def main():
     value = world * B * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the public API ("e2e") ---------------------------
+    gathered = torch.empty((world * B, n + ne + ni + 20), dtype=torch.float64, device="cuda") if world > 1 else None
+
     def e2e_step():
-        db.init(**host)          # H2D from pinned memory + Ruiz set-up kernel
+        db.init(**host)          # H2D from pinned memory (chunked, progress words); the set-up is fused into the solve kernel
         db.solve()               # persistent solve kernel
-        r = db.results()         # D2H of x, y, z, se, si + info
-        if world > 1:            # the one exchange step: gather the solutions
-            tx = torch.from_numpy(r["x"]).cuda()
-            out = [torch.empty_like(tx) for _ in range(world)] if rank == 0 else None
-            dist.gather(tx, out, dst=0)
-        return r
+        if world > 1:            # the one exchange step: gather (x, y, z, info) of every rank FROM THE DEVICE BUFFERS (NCCL)
+            rd = db.results_device()
+            dist.all_gather_into_tensor(gathered, torch.cat([rd["x"], rd["y"], rd["z"], rd["info"]], dim=1))
+        return db.results()      # D2H of this rank's x, y, z, se, si + info
     d2h_bytes = 8 * B * (n + 2 * ne + 2 * ni) + B * 20 * 8
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
@@ -328,7 +350,8 @@ def main():
         cpu = None
         b_alg = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline(sample=512, reps=5)
+            pin_openmp_env(host_threads())
+            cpu = cpu_baseline(sample=CPU_SAMPLE, reps=5)
             b_alg = algorithmic_bytes_per_qp(cpu["counters"], n, ne, ni, ni, cpu["sample"])
         else:
             try:
@@ -342,18 +365,28 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
+        ncu = {}
+        try:  # utilisation figures of the committed ncu --set full capture of this kernel (profiles/, per round)
+            with open(os.path.join(ROOT, "profiles", "ncu_solve_metrics.json")) as f:
+                ncu = json.load(f)
+        except Exception:
+            pass
         roof = None
         if b_alg is not None and kernel_ms > 0:
             achieved = b_alg * B / (kernel_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": peak_src, "kernel": "pqp_solve_kernel", "kernel_ms": kernel_ms,
                     "algorithmic_bytes_per_qp": b_alg, "compulsory_bytes_per_qp": compulsory_bytes_per_qp(n, ne, ni),
-                    "achieved_compulsory_gbs": compulsory_bytes_per_qp(n, ne, ni) * B / (kernel_ms * 1e-3) / 1e9}
+                    "achieved_compulsory_gbs": compulsory_bytes_per_qp(n, ne, ni) * B / (kernel_ms * 1e-3) / 1e9,
+                    "note": "three figures, never mixed: `achieved` uses the streamed-operand model B_alg of SURVEY 8(d)(ii) (what the CPU algorithm streams), "
+                            "`achieved_compulsory_gbs` the compulsory floor B_min, `traffic` the ncu-measured DRAM bytes per launch. The kernel keeps its factors on chip, "
+                            "so HBM is not its roof; `ncu` gives issue-slot / FP64-pipe utilisation of the same kernel",
+                    "ncu": ncu or None}
         line = {
             "metric": "QPs solved/sec (batch dense, n=100)", "value": value, "unit": "QPs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BatchQP {B} random dense QPs per GPU, n={n} n_eq={n_eq_str()} n_in={ni}, fp64, eps_abs=1e-9 eps_rel=0 NO_INITIAL_GUESS (BASELINE.json configs[1]; generator of benchmark/timings-parallel.cpp)",
+            "config": {"workload": f"BatchQP {B} random dense QPs per GPU, n={n} n_eq={n_eq_str()} n_in={ni}, fp64, eps_abs=1e-9 eps_rel=0 NO_INITIAL_GUESS (BASELINE.json configs[1]'s QP shape at the north-star batch of 4096; generator of benchmark/timings-parallel.cpp)",
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"batch sharded over {world} GPU(s), no collective in the iteration",
                        "e2e_mode": os.environ.get("PQP_E2E", "fused") + " (init uploads, the solve kernel equilibrates + solves each QP as its inputs arrive)",
                        "l2": "inputs larger than L2 (scaled+model data %.0f MB per GPU per step)" % (2 * h2d_bytes / 1e6)},
@@ -362,7 +395,8 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": None if cpu is None else {"value": cpu["qps"], "unit": "QPs/s", "cores": cpu["cores"], "kind": "port",
-                                                      "sample": f"{cpu['sample']} QPs of the same workload x {cpu['reps']} repetitions (best), OpenMP schedule(dynamic), {cpu['solved']}/{cpu['sample']} solved"},
+                                                      "sample": f"{cpu['sample']} QPs of the same workload x {cpu['reps']} repetitions (best), OpenMP schedule(dynamic), {cpu['solved']}/{cpu['sample']} solved; {cpu['flags']}",
+                                                      "times_ms": [round(1e3 * t, 2) for t in cpu["times"]], "threads_tried_ms": {str(k): round(1e3 * v, 2) for k, v in cpu["tried"].items()}},
         }
         print(json.dumps(line))
     if world > 1:

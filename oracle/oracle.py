@@ -38,6 +38,27 @@ BACKEND_AUTOMATIC, BACKEND_PRIMAL_DUAL_LDLT, BACKEND_PRIMAL_LDLT = 0, 1, 2
 HESSIAN_ZERO, HESSIAN_DENSE, HESSIAN_DIAGONAL = 0, 1, 2
 
 
+def use_native() -> str:
+    """bench.py only: rebuild the restatement with -march=native ON THE MACHINE THAT RUNS IT (the committed Makefile
+    targets x86-64-v3 so that the prebuilt library of the tests runs on any box) into oracle/_native/ and make this
+    module load that library. Falls back to the portable build if the compiler is missing. Returns the flags used."""
+    global _LIB_PATH, _lib
+    out_dir = os.path.join(_HERE, "_native")
+    out = os.path.join(out_dir, "liboracle.so")
+    flags = "-O3 -march=native -std=c++17 -fopenmp -fPIC -DNDEBUG"
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["/usr/bin/g++"] + flags.split() + ["-shared", "-o", out, os.path.join(_HERE, "oracle_capi.cpp")],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        C.CDLL(out)  # must load on this CPU
+    except Exception:
+        build()
+        return "-march=x86-64-v3 (portable build; native rebuild failed)"
+    _LIB_PATH = out
+    _lib = None
+    return flags
+
+
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (g++, no Eigen)."""
     srcs = ["oracle_capi.cpp", "proxqp_oracle.hpp", "proxqp_solver.hpp", "ldlt.hpp",

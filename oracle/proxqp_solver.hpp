@@ -4,6 +4,8 @@
 // the factorisation helpers of dense/helpers.hpp (file:line cited per
 // function, under /root/reference/include/proxsuite/proxqp).
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 
 namespace oracle {
 
@@ -1244,6 +1246,7 @@ qp_solve(QP& qp)
     res.info.pri_res = primal_feasibility_lhs;
     res.info.dua_res = dual_feasibility_lhs;
     res.info.duality_gap = duality_gap;
+    if (std::getenv("ORC_TRACE")) std::fprintf(stderr, "orc iter %lld pri %.4e dua %.4e mu_in %.1e status %d iter %lld\n", (long long)iter, primal_feasibility_lhs, dual_feasibility_lhs, res.info.mu_in, int(res.info.status), (long long)res.info.iter);
     double new_bcl_mu_in = res.info.mu_in, new_bcl_mu_eq = res.info.mu_eq;
     double new_bcl_mu_in_inv = res.info.mu_in_inv, new_bcl_mu_eq_inv = res.info.mu_eq_inv;
     double rhs_pri = scaled_eps;

@@ -1940,7 +1940,9 @@ __device__ void solve_one(Ctx& c, const PqpSolveArgs& A, int q)
       global_dual_residual(c, sc, g);
     }
     PROF_ADD(PH_GLOBAL, tph);
-    residuals_fresh = true;
+    // (not in closest-feasible mode: there the primal residual depends on info.status, which the end of this
+    // iteration may just have changed from PRIMAL_INFEASIBLE to SOLVED_CLOSEST_PRIMAL_FEASIBLE, utils.hpp:241-248)
+    residuals_fresh = !S.primal_infeasibility_solving;
     const double dual_feasibility_lhs_new = g.dua_lhs;
     info_dua = g.dua_lhs;
     info_gap = g.gap;

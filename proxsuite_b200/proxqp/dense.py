@@ -72,6 +72,7 @@ class _Group:
         self.key = (int(n), int(n_eq), int(n_in), bool(box), int(hessian), int(backend))
         self.n, self.n_eq, self.n_in, self.box = int(n), int(n_eq), int(n_in), bool(box)
         self.nc = self.n_in + (self.n if self.box else 0)
+        self.device = int(device)
         self.handle = self.lib.pqp_batch_create(self.capacity, self.n, self.n_eq, self.n_in, int(self.box), int(hessian), int(backend), int(device))
         if not self.handle:
             msg = _capi.last_error()
@@ -547,6 +548,31 @@ class DenseBatch:
         rec = np.frombuffer(info, dtype=_capi.INFO_DTYPE, count=self.batch)
         inf = {k: np.ascontiguousarray(rec[k]) for k in rec.dtype.names}
         return dict(x=x, y=y, z=z, se=se, si=si, info=inf)
+
+    def results_device(self):
+        """Zero-copy torch views of the solutions where the solve kernel wrote them (device memory of this batch):
+        dict(x[B, n], y[B, n_eq], z[B, n_cons], info[B, 20]); valid after sync() and until the next solve / init.
+        info columns follow pqp_info (6 iter, 7 iter_ext, 8 mu_updates, 10 status, 14 objValue, 15 pri_res, 16 dua_res).
+        Lets a caller hand the results to NCCL (sharding.solve_sharded) or to torch code without a host round trip."""
+        import torch
+
+        G = self._g
+        ptrs = [ct.c_void_p(0) for _ in range(4)]
+        _capi.check(G.lib.pqp_batch_results_device(G.handle, *[ct.byref(q) for q in ptrs]))
+        nc = G.n_in + (G.n if G.box else 0)
+
+        class _View:
+            def __init__(self, ptr, shape):
+                self.__cuda_array_interface__ = dict(shape=shape, typestr="<f8", data=(int(ptr), False), version=3, strides=None)
+
+        dev = torch.device("cuda", G.device if G.device >= 0 else torch.cuda.current_device())
+        out = {}
+        for name, q, w in (("x", ptrs[0], G.n), ("y", ptrs[1], G.n_eq), ("z", ptrs[2], nc), ("info", ptrs[3], 20)):
+            if w == 0 or not q.value:
+                out[name] = torch.empty((self.batch, 0), dtype=torch.float64, device=dev)
+            else:
+                out[name] = torch.as_tensor(_View(q.value, (self.batch, w)), device=dev)
+        return out
 
     def timings(self):
         return self._g.timings()

@@ -1,0 +1,210 @@
+"""GPU parity at the EXACT shapes of BASELINE.json's configs (reduced batch), through the C-ABI, against the
+oracle on the same seeded inputs: identical status, KKT residuals recomputed from the ORIGINAL data <= 1e-9,
+|x_gpu - x_oracle|_inf <= 1e-6 max(1, |x|_inf), and the same iteration counters (iter, iter_ext, mu_updates).
+Plus the rows of SURVEY.md section 8 that had no hardware test in round 1: the PrimalLDLT backend shape
+(test/src/dense_qp_wrapper.cpp:7618-7673), dual infeasibility (dense/utils.hpp:345-419) and the closest-feasible
+mode (dense/solver.hpp:1572-1595, test/src/dense_qp_wrapper.cpp:7153-7210). Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+from helpers import kkt_residuals
+
+pytestmark = pytest.mark.gpu
+
+EPS = 1e-9
+XTOL = 1e-6
+KEYS = "HgAbClu"
+
+
+@pytest.fixture(scope="module")
+def px():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from proxsuite_b200 import proxqp
+
+    return proxqp
+
+
+def batch_vs_oracle(px, oracle, kind, B, n, ne, ni, box=False, hessian=1, sparsity=0.15, counters=True, first_seed=0):
+    """One DenseBatch of B QPs (seeds first_seed..) against B oracle solves."""
+    data = [oracle.generate_qp(kind, first_seed + i, n, ne, ni, sparsity) for i in range(B)]
+    keys = list(KEYS) + (["l_box", "u_box"] if box else [])
+    st = {k: np.stack([d[k] for d in data]) for k in keys}
+    db = px.dense.DenseBatch(B, n, ne, ni, box_constraints=box, hessian_type=px.HessianType(hessian))
+    db.settings.eps_abs = EPS
+    db.settings.eps_rel = 0
+    db.settings.initial_guess = px.InitialGuess.NO_INITIAL_GUESS
+    db.init(**st)
+    db.solve()
+    r = db.results()
+    cfg = db.launch_config()
+    for i, d in enumerate(data):
+        qo = oracle.OracleQP(n, ne, ni, box_constraints=box, hessian_type=hessian)
+        qo.set(eps_abs=EPS, eps_rel=0, initial_guess=oracle.NO_INITIAL_GUESS)
+        qo.init(**{k: d[k] for k in keys})
+        ro = qo.solve()
+        inf = r["info"]
+        assert int(inf["status"][i]) == ro.info.status == 0, (kind, i, int(inf["status"][i]), ro.info.status)
+        pri, dua = kkt_residuals(d, r["x"][i], r["y"][i], r["z"][i])
+        assert pri <= EPS and dua <= EPS, (kind, i, pri, dua)
+        assert np.abs(r["x"][i] - ro.x).max() <= XTOL * max(1.0, np.abs(ro.x).max()), (kind, i)
+        if counters:
+            got = (int(inf["iter"][i]), int(inf["iter_ext"][i]), int(inf["mu_updates"][i]))
+            want = (ro.info.iter, ro.info.iter_ext, ro.info.mu_updates)
+            assert got == want, (kind, i, got, want)
+    return cfg
+
+
+def test_cfg2_headline_shape_against_oracle(px, oracle):
+    # BASELINE.json configs[1] / north_star shape: benchmark/timings-parallel.cpp:19-54
+    cfg = batch_vs_oracle(px, oracle, "strongly_convex", 64, 100, 50, 100)
+    assert cfg["overflow_retries"] == 0
+
+
+def test_cfg3_box_constraint_shape_against_oracle(px, oracle):
+    # BASELINE.json configs[2]: benchmark/timings-box-constraints.cpp:25-95 (n=100, n_eq=50, n_in=50, box)
+    batch_vs_oracle(px, oracle, "box_benchmark", 32, 100, 50, 50, box=True, sparsity=0.75)
+
+
+def test_cfg4_n256_shape_against_oracle(px, oracle):
+    # BASELINE.json configs[3]: n=256, n_eq=128, n_in=256 (the multi-GPU config, per-GPU kernel path)
+    batch_vs_oracle(px, oracle, "strongly_convex", 8, 256, 128, 256)
+
+
+def test_cfg5_diagonal_hessian_n500_against_oracle(px, oracle):
+    # BASELINE.json configs[4]: benchmark/timings-diagonal-hessian.cpp:25-105 (n=500, diagonal H with H_00 = 0, box)
+    batch_vs_oracle(px, oracle, "diagonal_benchmark", 3, 500, 250, 250, box=True, hessian=2, sparsity=0.75)
+
+
+def test_primal_ldlt_backend_shape(px, oracle):
+    """test/src/dense_qp_wrapper.cpp:7618-7673: dim 3, 9 inequalities, sparsity 1, DenseBackend::PrimalLDLT,
+    eps_abs 1e-7: mu_updates > 0 and residuals <= eps. Then the timings-dense-backend shape (n_eq = n_in = 2 n) with
+    PrimalLDLT and Automatic against the oracle's PrimalLDLT backend."""
+    d = oracle.generate_qp("strongly_convex", 1, 3, 0, 9, 1.0)
+    qp = px.dense.QP(3, 0, 9, False, px.HessianType.Dense, px.DenseBackend.PrimalLDLT)
+    qp.settings.eps_abs = 1e-7
+    qp.settings.eps_rel = 0
+    qp.init(d["H"], d["g"], None, None, d["C"], None, d["u"])
+    qp.solve()
+    r = qp.results
+    assert int(r.info.status) == 0 and r.info.mu_updates > 0
+    d1 = dict(d, A=np.zeros((0, 3)), b=np.zeros(0), l=np.full(9, -1e20))
+    pri, dua = kkt_residuals(d1, r.x, r.y, r.z)
+    assert pri <= 1e-7 and dua <= 1e-7
+    qo = oracle.OracleQP(3, 0, 9, dense_backend=oracle.BACKEND_PRIMAL_LDLT)
+    qo.set(eps_abs=1e-7, eps_rel=0)
+    qo.init(H=d["H"], g=d["g"], C=d["C"], u=d["u"])
+    ro = qo.solve()
+    assert ro.info.status == 0 and ro.info.mu_updates > 0
+    assert np.abs(r.x - ro.x).max() <= XTOL * max(1.0, np.abs(ro.x).max())
+    # benchmark/timings-dense-backend.cpp:27-28, 67: n_eq = n_in = 2 n -> the Automatic heuristic picks PrimalLDLT
+    n = 20
+    for seed in (0, 1):
+        d = oracle.generate_qp("strongly_convex", seed, n, 2 * n, 2 * n, 0.15)
+        for backend, ob in ((px.DenseBackend.PrimalLDLT, oracle.BACKEND_PRIMAL_LDLT), (px.DenseBackend.Automatic, oracle.BACKEND_AUTOMATIC)):
+            qp = px.dense.QP(n, 2 * n, 2 * n, False, px.HessianType.Dense, backend)
+            qp.settings.eps_abs = EPS
+            qp.settings.eps_rel = 0
+            qp.init(*[d[k] for k in KEYS])
+            qp.solve()
+            qo = oracle.OracleQP(n, 2 * n, 2 * n, dense_backend=ob)
+            qo.set(eps_abs=EPS, eps_rel=0)
+            qo.init(**{k: d[k] for k in KEYS})
+            ro = qo.solve()
+            assert int(qp.results.info.status) == ro.info.status
+            if ro.info.status == 0:
+                pri, dua = kkt_residuals(d, qp.results.x, qp.results.y, qp.results.z)
+                assert pri <= EPS and dua <= EPS
+                assert np.abs(qp.results.x - ro.x).max() <= XTOL * max(1.0, np.abs(ro.x).max())
+                assert qp.results.info.rho == ro.info.rho  # the PrimalLDLT default rho travels (wrapper.hpp:186-190)
+
+
+def test_dual_infeasibility_is_detected(px, oracle):
+    """dense/utils.hpp:345-419: an unbounded direction (zero curvature, negative cost, no bound) must end in
+    PROXQP_DUAL_INFEASIBLE with the oracle's certificate and iteration count."""
+    cases = [
+        (np.zeros((2, 2)), np.array([-1.0, 0.0]), np.array([[0.0, 1.0]]), np.array([-1e20]), np.array([1.0])),
+        (np.diag([0.0, 1.0]), np.array([-1.0, 0.0]), np.array([[0.0, 1.0]]), np.array([-1e20]), np.array([1.0])),
+        (np.diag([1.0, 0.0, 2.0]), np.array([0.5, 2.0, -1.0]), np.array([[1.0, 0.0, 1.0], [1.0, 0.0, -1.0]]), np.array([-1.0, -1e20]), np.array([1.0, 3.0])),
+    ]
+    for H, g, C, l, u in cases:
+        n, ni = g.size, C.shape[0]
+        hess = px.HessianType.Zero if not H.any() else px.HessianType.Dense
+        qp = px.dense.QP(n, 0, ni, False, hess)
+        qp.settings.eps_abs = EPS
+        qp.settings.eps_rel = 0
+        qp.init(H, g, None, None, C, l, u)
+        qp.solve()
+        qo = oracle.OracleQP(n, 0, ni, hessian_type=int(hess))
+        qo.set(eps_abs=EPS, eps_rel=0)
+        qo.init(H=H, g=g, C=C, l=l, u=u)
+        ro = qo.solve()
+        assert ro.info.status == oracle.PROXQP_DUAL_INFEASIBLE
+        assert qp.results.info.status == px.QPSolverOutput.PROXQP_DUAL_INFEASIBLE
+        assert qp.results.info.iter == ro.info.iter
+        # the certificate (the unscaled step dx) is what both return in x
+        assert np.allclose(qp.results.x, ro.x, rtol=1e-6, atol=1e-9)
+
+
+def test_closest_feasible_mode(px, oracle):
+    """primal_infeasibility_solving (dense/solver.hpp:1572-1595, utils.hpp:241-248).
+    (a) test/src/dense_qp_wrapper.cpp:7153-7210 (b += 10, u -= 100 on seeded QPs, eps 1e-5): the reference's two
+    residual criteria and the oracle's status / iteration counts. (b) genuinely infeasible QPs (the reference's
+    infeasible QP of test/src/dense_qp_eq.cpp:217-258 and an inconsistent pair of equality rows): same x and
+    slacks as the oracle."""
+    n, ne, ni = 20, 5, 5
+    eps = 1e-5
+    for seed in range(6):
+        d = oracle.generate_qp("strongly_convex", seed, n, ne, ni, 0.15)
+        d["b"] = d["b"] + 10.0
+        d["u"] = d["u"] - 100.0
+        # max_iter: once the closest feasible point is found the reference keeps iterating to max_iter (the top-of-loop
+        # residual is evaluated with status SOLVED_CLOSEST_PRIMAL_FEASIBLE, i.e. in plain mode); 60 keeps that short
+        st = dict(eps_abs=eps, eps_rel=0.0, primal_infeasibility_solving=True, eps_primal_inf=1e-4, eps_dual_inf=1e-4, max_iter=60)
+        qp = px.dense.QP(n, ne, ni)
+        for k, v in st.items():
+            setattr(qp.settings, k, v)
+        qp.settings.initial_guess = px.InitialGuess.NO_INITIAL_GUESS
+        qp.init(*[d[k] for k in KEYS])
+        qp.solve()
+        qo = oracle.OracleQP(n, ne, ni)
+        qo.set(initial_guess=oracle.NO_INITIAL_GUESS, **{k: float(v) for k, v in st.items()})
+        qo.init(**{k: d[k] for k in KEYS})
+        ro = qo.solve()
+        r = qp.results
+        assert int(r.info.status) == ro.info.status, (seed, int(r.info.status), ro.info.status)
+        scaled_eps = np.abs(d["A"].T @ np.ones(ne) + d["C"].T @ np.ones(ni)).max() * eps
+        cx = d["C"] @ r.x
+        pri = np.abs(d["A"].T @ (d["A"] @ r.x - d["b"]) + d["C"].T @ (np.maximum(cx - d["u"], 0) + np.minimum(cx - d["l"], 0))).max()
+        dua = np.abs(d["H"] @ r.x + d["g"] + d["A"].T @ r.y + d["C"].T @ r.z).max()
+        assert pri <= scaled_eps and dua <= eps, (seed, pri, scaled_eps, dua)
+        assert np.abs(r.x - ro.x).max() <= 1e-4 * max(1.0, np.abs(ro.x).max())
+        assert r.info.iter == ro.info.iter and r.info.iter_ext == ro.info.iter_ext
+    H = 2 * np.eye(2)
+    C = np.array([[1.0, 0.0], [0.0, 1.0], [-1.0, 0.0]])
+    kw1 = dict(H=H, g=np.array([-18.0, -12.0]), C=C, l=np.full(3, -1e20), u=np.array([10.0, 10.0, -20.0]))
+    d = oracle.generate_qp("strongly_convex", 7, 8, 4, 5, 0.6, 1e-1)
+    A, b = d["A"].copy(), d["b"].copy()
+    A[3] = A[0]
+    b[3] = b[0] + 1.0
+    kw2 = dict(H=d["H"], g=d["g"], A=A, b=b, C=d["C"], l=d["l"], u=d["u"])
+    for dims, kw in (((2, 0, 3), kw1), ((8, 4, 5), kw2)):
+        qp = px.dense.QP(*dims)
+        qp.settings.eps_abs = EPS
+        qp.settings.eps_rel = 0
+        qp.settings.primal_infeasibility_solving = True
+        qp.settings.max_iter = 60
+        qp.init(kw["H"], kw["g"], kw.get("A"), kw.get("b"), kw["C"], kw["l"], kw["u"])
+        qp.solve()
+        r = qp.results
+        qo = oracle.OracleQP(*dims)
+        qo.set(eps_abs=EPS, eps_rel=0, primal_infeasibility_solving=1, max_iter=60)
+        qo.init(**kw)
+        ro = qo.solve()
+        # which of the three "done" states is reported depends on rounding-level quantities here (the certificate
+        # test divides by |dz| -> 0 once the closest feasible point is reached): x and the slacks are the contract
+        ok_states = (oracle.PROXQP_SOLVED, oracle.PROXQP_SOLVED_CLOSEST_PRIMAL_FEASIBLE, oracle.PROXQP_PRIMAL_INFEASIBLE)
+        assert int(r.info.status) in ok_states and ro.info.status in ok_states
+        assert np.abs(r.x - ro.x).max() <= XTOL * max(1.0, np.abs(ro.x).max())
+        assert np.abs(r.si - ro.si).max() <= XTOL and (dims[1] == 0 or np.abs(r.se - ro.se).max() <= XTOL)
