@@ -128,16 +128,52 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def cpu_quota():
+    """CPUs' worth of time the cgroup lets this process use per period (cpu.max: "quota period"), or None.
+    The pool's GPU boxes show 128 logical CPUs in the affinity mask but a quota of 16: every thread beyond the quota only
+    burns it faster, and CFS then stops ALL threads until the next 100 ms period - which is what made round 1's
+    `--impl reference` arm 3.8x slower than the cpu_baseline leg of the same box (step times in multiples of 100 ms)."""
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, per = open(path).read().split()[:2]
+            if q != "max":
+                return float(q) / float(per)
+        except (OSError, ValueError):
+            pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return q / per
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+def thread_candidates():
+    """Thread counts worth trying for the CPU arm: every logical CPU, half of them (the reference's default,
+    parallel/qp_solve.hpp:45-49), and - under a cgroup CPU quota - the quota and twice the quota."""
+    H = host_threads()
+    c = {H, max(1, H // 2)}
+    q = cpu_quota()
+    if q:
+        c |= {max(1, min(H, int(q + 0.999))), max(1, min(H, 2 * int(q + 0.999)))}
+    return sorted(c, reverse=True)
+
+
 def pin_openmp_env(threads):
     """OpenMP environment of the CPU arm, set BEFORE libgomp is loaded (it reads the environment once): one thread per
     logical CPU, no migration, spinning workers. torchrun / the driver may export OMP_NUM_THREADS=1; the CPU arm must not
     inherit that."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
-    os.environ["OMP_PROC_BIND"] = "true"
-    os.environ["OMP_PLACES"] = "threads"
-    os.environ["OMP_WAIT_POLICY"] = "active"
     os.environ["OMP_DYNAMIC"] = "false"
     os.environ.pop("OMP_THREAD_LIMIT", None)
+    if cpu_quota() is None:  # (under a quota fewer threads than CPUs run: let the kernel place them; spinning would burn quota)
+        os.environ["OMP_PROC_BIND"] = "true"
+        os.environ["OMP_PLACES"] = "threads"
+        os.environ["OMP_WAIT_POLICY"] = "active"
+    else:
+        os.environ["OMP_WAIT_POLICY"] = "passive"
 
 
 def make_oracle_batch(sample):
@@ -178,7 +214,7 @@ def cpu_baseline(sample, reps, threads=0):
     if threads:
         T = threads
     else:
-        T, tried = best_thread_count(b, sorted({H, max(1, H // 2)}, reverse=True))
+        T, tried = best_thread_count(b, thread_candidates())
     b.solve(T)  # warm-up
     b.counters(reset=True)
     times = [b.solve(T) for _ in range(reps)]
@@ -202,7 +238,7 @@ def run_reference(args, rank, world):
     H = host_threads()
     pin_openmp_env(H)
     b, flags = make_oracle_batch(sample)
-    T, tried = best_thread_count(b, sorted({H, max(1, H // 2)}, reverse=True))
+    T, tried = best_thread_count(b, thread_candidates())
     for _ in range(max(args.warmup, 3)):
         b.solve(T)
     times = [b.solve(T) for _ in range(args.steps)]  # orc_batch_solve returns the wall time of the parallel region
@@ -222,7 +258,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": qps, "unit": "QPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "steps_ms": [round(1e3 * t, 2) for t in times], "best_step_qps": sample / min(times), "host_threads": H,
-        "threads_tried_ms": {str(k): round(1e3 * v, 2) for k, v in tried.items()}, "loadavg": load,
+        "threads_tried_ms": {str(k): round(1e3 * v, 2) for k, v in tried.items()}, "loadavg": load, "cgroup_cpu_quota": cpu_quota(),
     }
     print(json.dumps(line))
 
@@ -396,7 +432,8 @@ def main():
             "roofline": roof,
             "cpu_baseline": None if cpu is None else {"value": cpu["qps"], "unit": "QPs/s", "cores": cpu["cores"], "kind": "port",
                                                       "sample": f"{cpu['sample']} QPs of the same workload x {cpu['reps']} repetitions (best), OpenMP schedule(dynamic), {cpu['solved']}/{cpu['sample']} solved; {cpu['flags']}",
-                                                      "times_ms": [round(1e3 * t, 2) for t in cpu["times"]], "threads_tried_ms": {str(k): round(1e3 * v, 2) for k, v in cpu["tried"].items()}},
+                                                      "times_ms": [round(1e3 * t, 2) for t in cpu["times"]], "threads_tried_ms": {str(k): round(1e3 * v, 2) for k, v in cpu["tried"].items()},
+                                                      "host_threads": cpu["host_threads"], "cgroup_cpu_quota": cpu_quota()},
         }
         print(json.dumps(line))
     if world > 1:

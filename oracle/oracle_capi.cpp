@@ -91,6 +91,7 @@ orc_qp_get(void* p, const char* name)
     I(primal_infeasibility_solving) I(frequence_infeasibility_check)
 #undef I
       if (std::strcmp(name, "dense_backend") == 0) return double(qp.dense_backend);
+  if (std::strcmp(name, "max_nc") == 0) return double(qp.work.max_nc);
   return std::numeric_limits<double>::quiet_NaN();
 }
 

@@ -1150,6 +1150,7 @@ active_set_from_z(QP& qp)
   Workspace& w = qp.work;
   isize ncons = qp.n_constraints();
   w.n_c = 0;
+  w.max_nc = 0;
   for (isize i = 0; i < ncons; ++i) {
     w.active_inequalities[std::size_t(i)] = qp.results.z[std::size_t(i)] != 0 ? 1 : 0;
   }

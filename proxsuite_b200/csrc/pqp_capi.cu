@@ -94,6 +94,8 @@ struct pqp_batch
   int32_t* d_ready = nullptr;  // [0] QPs uploaded so far, [1] abort flag
   int32_t* h_ready = nullptr;  // pinned: cumulative QP count behind each upload chunk
   cudaEvent_t ev_feed = nullptr;
+  cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr; // around the retry launches of a sync()
+  float retry_ms = 0;                           // device time of the retry launches of the last solve
   // QPLayer backward (allocated on first use): loss derivatives in, BackwardData out
   double *bw_loss = nullptr, *bw_dH = nullptr, *bw_dg = nullptr, *bw_dA = nullptr, *bw_db = nullptr, *bw_dC = nullptr, *bw_du = nullptr, *bw_dl = nullptr;
 };
@@ -185,6 +187,7 @@ fill_layout(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, bool want_m1, 
   const int ncols = (n <= 128 && cap <= 128) ? 128 : ((n <= 160 && cap <= 160) ? 160 : 256);
   vsz[V_SCRATCH] = std::max<int>(PQP_NW * ncols, (n <= 256 && (n % 2) == 0) ? PQP_NW * n : PQP_NT);
   vsz[V_SCRATCH] = std::max<int>(vsz[V_SCRATCH], 8 * ((std::max(n, cap) + 2) & ~1)); // 8 panel vectors of the blocked sweep
+  vsz[V_SCRATCH] = std::max<int>(vsz[V_SCRATCH], PQP_NW * (std::max(n, cap) + 2));     // NW partial vectors of the any-n row passes / symmetric mat-vec
   vsz[V_RED] = PQP_NW * 16; // block_reduce: up to 10 values per warp
   vsz[V_KT] = 2;
   vsz[V_KT2] = 2;
@@ -271,11 +274,21 @@ fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_ca
   vsz[V_RED] = PQP_NW * 16;
   vsz[V_KT] = ne + nc + 4;
   vsz[V_KT2] = ne + nc + 4;
+  // Arena diet (every double saved here is S^-1 capacity: cfg 2 needs 113 slots for seeds 0..4095, 111 fitted):
+  //   s4 is unused by the tile kernel; t3 (C^T z of the global passes) and q (per Newton step) are never live together;
+  //   kt2 (second coefficient vector of the global passes) and alphas (line search breakpoints) neither.
+  const bool alias_kt2 = vsz[V_ALPHAS] >= vsz[V_KT2];
+  vsz[V_S4] = 0;
+  vsz[V_T3] = 0;
+  if (alias_kt2) vsz[V_KT2] = 0;
   int off = 0;
   for (int v = 0; v < V_COUNT; ++v) {
     L.voff[v] = off;
     off += (int)rnd(vsz[v]);
   }
+  L.voff[V_S4] = L.voff[V_S3];
+  L.voff[V_T3] = L.voff[V_Q];
+  if (alias_kt2) L.voff[V_KT2] = L.voff[V_ALPHAS];
   L.voff[V_RUP] = L.voff[V_SE] + ne;
   L.voff[V_CDX] = L.voff[V_ADX] + ne;
   L.vec_doubles = off;
@@ -914,7 +927,7 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
     b->hinfo[i].status = PQP_NOT_RUN;
   }
   bool aux_ok = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&b->ev_main, cudaEventDisableTiming) == cudaSuccess &&
-                cudaEventCreateWithFlags(&b->ev_feed, cudaEventDisableTiming) == cudaSuccess;
+                cudaEventCreateWithFlags(&b->ev_feed, cudaEventDisableTiming) == cudaSuccess && cudaEventCreate(&b->ev_r0) == cudaSuccess && cudaEventCreate(&b->ev_r1) == cudaSuccess;
   for (int k = 0; k < PQP_UPLOAD_CHUNKS; ++k) aux_ok = aux_ok && cudaEventCreateWithFlags(&b->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < PQP_CSTREAMS; ++k)
     aux_ok = aux_ok && cudaStreamCreateWithFlags(&b->cstream[k], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&b->ev_cdone[k], cudaEventDisableTiming) == cudaSuccess;
@@ -982,6 +995,8 @@ pqp_batch_destroy(pqp_batch* b)
   if (b->ev3) cudaEventDestroy(b->ev3);
   if (b->ev_main) cudaEventDestroy(b->ev_main);
   if (b->ev_feed) cudaEventDestroy(b->ev_feed);
+  if (b->ev_r0) cudaEventDestroy(b->ev_r0);
+  if (b->ev_r1) cudaEventDestroy(b->ev_r1);
   if (b->h_ready) cudaFreeHost(b->h_ready);
   for (int k = 0; k < PQP_UPLOAD_CHUNKS; ++k)
     if (b->ev_chunk[k]) cudaEventDestroy(b->ev_chunk[k]);
@@ -1233,6 +1248,7 @@ pqp_batch_sync(pqp_batch* b)
         if (b->hparams[i].active && raw[(size_t)i * PQP_INFO_DOUBLES + 10] == 99.0) retry.push_back(i);
       }
       if (!retry.empty()) b->overflow_retries += (int64_t)retry.size();
+      b->retry_ms = 0;
       // level 1: the tile kernel with its largest capacity (one CTA per SM); level 2: the general kernel
       for (int level = (b->lay_big.kind == 1 ? 1 : 2); level <= 2 && !retry.empty(); ++level) {
         std::vector<int32_t> saved((size_t)b->B);
@@ -1241,11 +1257,18 @@ pqp_batch_sync(pqp_batch* b)
           b->hparams[i].active = 0;
         }
         for (int64_t i : retry) b->hparams[i].active = 1;
-        int rc = (level == 1) ? enqueue_solve(b, b->stream, b->lay_big, b->grid_big) : enqueue_solve(b, b->stream, b->lay_gen, b->grid_gen);
+        // (not `timed`: the events of the main launch must survive; the retry launches are timed on their own pair and added)
+        CUDA_TRY(cudaEventRecord(b->ev_r0, b->stream));
+        int rc = (level == 1) ? enqueue_solve(b, b->stream, b->lay_big, b->grid_big, 0, -1, 0, false) : enqueue_solve(b, b->stream, b->lay_gen, b->grid_gen, 0, -1, 0, false);
         for (int64_t i = 0; i < b->B; ++i) b->hparams[i].active = saved[i];
         if (rc != 0) return rc;
+        CUDA_TRY(cudaEventRecord(b->ev_r1, b->stream));
         b->launches += 1;
         CUDA_TRY(cudaStreamSynchronize(b->stream));
+        {
+          float ms_r = 0;
+          if (cudaEventElapsedTime(&ms_r, b->ev_r0, b->ev_r1) == cudaSuccess) b->retry_ms += ms_r;
+        }
         CUDA_TRY(cudaMemcpy(raw.data(), b->p.info, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost));
         std::vector<int64_t> still;
         for (int64_t i : retry) {
@@ -1256,6 +1279,7 @@ pqp_batch_sync(pqp_batch* b)
     }
     float ms_solve = 0, ms_setup = 0;
     if (b->solve_timed) cudaEventElapsedTime(&ms_solve, b->ev2, b->ev3);
+    ms_solve += b->retry_ms;
     if (b->setup_timed) cudaEventElapsedTime(&ms_setup, b->ev0, b->ev1);
     int64_t nact = 0;
     for (int64_t i = 0; i < b->B; ++i) nact += b->hparams[i].active ? 1 : 0;
@@ -1501,7 +1525,7 @@ pqp_batch_timings(const pqp_batch* b, double* setup_ms, double* solve_ms, int64_
   }
   if (solve_ms) {
     *solve_ms = 0;
-    if (b->solve_timed && cudaEventElapsedTime(&ms, b->ev2, b->ev3) == cudaSuccess) *solve_ms = ms;
+    if (b->solve_timed && cudaEventElapsedTime(&ms, b->ev2, b->ev3) == cudaSuccess) *solve_ms = ms + b->retry_ms; // main launch + retry launches
   }
   if (launches) *launches = b->launches;
   return 0;

@@ -291,15 +291,33 @@ __device__ void axpy_pass_t(const Ctx& c, const double* __restrict__ base0, int 
       }
     }
   }
-  _Pragma("unroll 1") for (; k < nrows; k += NW) {
-    double cf;
-    const double2* rp = rowptr(k, cf);
+  // remainder (fewer than UNR rows of this warp): ONE more batch with the loads of all its rows in flight together
+  // (a row-at-a-time tail costs one L2 round trip per row: up to five in a 100-row pass, against two for the batches)
+  if (k < nrows) {
+    const double2* rp[UNR];
+    double cf[UNR];
+    double2 v[UNR][NCH];
+    bool rv[UNR];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      if (pv[ch]) {
-        const double2 v = rp[32 * ch];
-        acc[ch].x = fma(cf, v.x, acc[ch].x);
-        acc[ch].y = fma(cf, v.y, acc[ch].y);
+    for (int u = 0; u < UNR; ++u) {
+      rv[u] = k + u * NW < nrows;
+      cf[u] = 0.0;
+      rp[u] = nullptr;
+      if (rv[u]) rp[u] = rowptr(k + u * NW, cf[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) v[u][ch] = (rv[u] && pv[ch]) ? rp[u][32 * ch] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (rv[u]) { // (skipping keeps the sum bit-identical to the row-at-a-time form: no 0 * x terms are added)
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          acc[ch].x = fma(cf[u], v[u][ch].x, acc[ch].x);
+          acc[ch].y = fma(cf[u], v[u][ch].y, acc[ch].y);
+        }
       }
     }
   }
@@ -1786,12 +1804,17 @@ __device__ PQP_SOLVE_ONE_ATTR void solve_one(Ctx& c, const PqpSolveArgs& A, int 
           if (expired) break;
         }
         // -- Newton step (solver.hpp:756-869)
+        int changed = 0;
         _Pragma("unroll 1") for (int i = tid; i < nc; i += NT) {
-          c.act_up[i] = v_rup[i] >= 0.0;
-          c.act_low[i] = v_si[i] <= 0.0;
+          const bool up = v_rup[i] >= 0.0, low = v_si[i] <= 0.0;
+          c.act_up[i] = up;
+          c.act_low[i] = low;
+          changed |= ((up || low) != (c.cons_slot[i] >= 0)) ? 1 : 0;
         }
-        __syncthreads();
-        active_set_change(c, sc);
+        // (the barrier doubles as the vote: most late Newton steps keep the active set, and then the two ordered
+        // compactions of active_set_change - four barriers - are skipped; c.si_valid is block-uniform here)
+        changed = __syncthreads_or(changed);
+        if (changed || !c.si_valid) active_set_change(c, sc);
         if (c.overflow) { // S^-1 capacity exceeded: the QP is re-solved by the generic kernel
           expired = true;
           break;

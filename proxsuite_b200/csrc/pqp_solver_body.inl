@@ -297,15 +297,55 @@ __device__ void sym_mv_fast(const Ctx& c, const double* __restrict__ T, const do
   __syncthreads();
 }
 
-// any n (slow, only for shapes beyond the fast paths)
-__device__ void sym_mv_generic(const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n)
+// any n (shapes beyond the register-resident fast paths: cfg 4 / cfg 5 dual blocks). Packed lower storage:
+//   y_i = sum_{j <= i} T[i][j] x_j  (row part: a warp owns row i, coalesced loads, one warp reduction)
+//       + sum_{i' > i} T[i'][i] x_i' (column part, AXPY form: lane-stationary accumulators for a group of 256 columns)
+// Columns are processed in groups of 256 so that the accumulators stay in registers; the partial vectors of the NW
+// warps are combined through c.scratch (NW x n doubles). Row i belongs to the same lane-0 thread in every group
+// (256 is a multiple of NW), so the row sums accumulate in a fixed order: results do not depend on scheduling.
+__device__ void sym_mv_generic(const Ctx& c, const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n)
 {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* const scr = c.scratch;
+  _Pragma("unroll 1") for (int g0 = 0; g0 < n; g0 += 256) {
+    double acc[8], xl[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const int j = g0 + lane + 32 * cc;
+      acc[cc] = 0.0;
+      xl[cc] = (j < n) ? x[j] : 0.0;
+    }
+    _Pragma("unroll 1") for (int i = g0 + warp; i < n; i += NW) {
+      const double* row = T + (size_t)i * (size_t)(i + 1) / 2;
+      const double xi = x[i];
+      double a[8];
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const int j = g0 + lane + 32 * cc;
+        a[cc] = (j <= i) ? row[j] : 0.0;
+      }
+      double d = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const int j = g0 + lane + 32 * cc;
+        d = fma(a[cc], xl[cc], d);
+        if (j < i) acc[cc] = fma(a[cc], xi, acc[cc]);
+      }
+      d = warp_sum(d);
+      if (lane == 0) y[i] = (g0 == 0) ? d : y[i] + d;
+    }
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const int j = g0 + lane + 32 * cc;
+      if (j < n) scr[(size_t)warp * n + j] = acc[cc];
+    }
+  }
+  __syncthreads();
   _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
-    double a = 0;
-    const double* rj = T + (size_t)j * (size_t)(j + 1) / 2;
-    for (int i = 0; i <= j; ++i) a += rj[i] * x[i];
-    for (int i = j + 1; i < n; ++i) a += T[(size_t)i * (size_t)(i + 1) / 2 + j] * x[i];
-    y[j] = a;
+    double sacc = y[j];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sacc += scr[(size_t)w * n + j];
+    y[j] = sacc;
   }
   __syncthreads();
 }
@@ -320,14 +360,14 @@ __device__ __noinline__ void sym_mv(const Ctx& c, const double* T, const double*
     else if (n <= 256)
       sym_mv_fast<8, true>(c, T, x, y, n);
     else
-      sym_mv_generic(T, x, y, n);
+      sym_mv_generic(c, T, x, y, n);
   } else {
     if (n <= 128)
       sym_mv_fast<4, false>(c, T, x, y, n);
     else if (n <= 256)
       sym_mv_fast<8, false>(c, T, x, y, n);
     else
-      sym_mv_generic(T, x, y, n);
+      sym_mv_generic(c, T, x, y, n);
   }
 }
 
@@ -740,36 +780,103 @@ __device__ void rows_dot(const Ctx& c, RowSrc rs, int r0, int r1, const double* 
   PQP_VECS(c);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = c.n;
-  for (int r = r0 + warp; r < r1; r += NW) {
-    int bk, idx;
-    const double* row = get_row(c, rs, r, bk, idx);
-    double acc;
-    if (row) {
-      double a0 = 0;
-      for (int j = lane; j < n; j += 32) a0 += row[j] * x[j];
-      acc = warp_sum(a0);
-    } else {
-      acc = v_is[bk] * x[bk];
+  // four rows of a warp in flight (one row at a time is one L2 round trip per 32 columns of every row)
+  _Pragma("unroll 1") for (int rb = r0 + warp; rb < r1; rb += 4 * NW) {
+    const double* rowp[4];
+    int bk[4], idx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * NW;
+      rowp[u] = nullptr;
+      bk[u] = -1;
+      idx[u] = -1;
+      if (r < r1) rowp[u] = get_row(c, rs, r, bk[u], idx[u]);
     }
-    if (lane == 0) out[idx] = acc;
+    double d[4] = { 0.0, 0.0, 0.0, 0.0 };
+    _Pragma("unroll 2") for (int j = lane; j < n; j += 32) {
+      const double xj = x[j];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = rowp[u] ? rowp[u][j] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d[u] = fma(v[u], xj, d[u]);
+    }
+    reduce_rows<4>(d, lane);
+    if ((lane & 7) == 0) {
+      const int u = lane >> 3;
+      const int id = (u == 0) ? idx[0] : (u == 1) ? idx[1] : (u == 2) ? idx[2] : idx[3];
+      const int bb = (u == 0) ? bk[0] : (u == 1) ? bk[1] : (u == 2) ? bk[2] : bk[3];
+      if (id >= 0) out[id] = (bb < 0) ? d[0] : v_is[bb] * x[bb];
+    }
   }
   __syncthreads();
 }
+// out[j] = add[j] + sign * sum_r coef[idx(r)] row_r[j], any n: warp w owns rows r0 + w + NW k (two in flight), a lane
+// owns the columns lane + 32 cc of a 256-column group (register accumulators), the NW partial vectors are combined
+// through c.scratch (NW x n doubles). (The first version gave every thread one column and walked all rows
+// sequentially: one dependent L2 round trip per row - cfg 5 spent seconds per QP there.)
 __device__ void rows_axpy_t(const Ctx& c, RowSrc rs, int r0, int r1, const double* __restrict__ coef, double* out, const double* add, double sign)
 {
   PQP_VECS(c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = c.n;
-  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
-    double acc = 0;
-    for (int r = r0; r < r1; ++r) {
-      int bk, idx;
-      const double* row = get_row(c, rs, r, bk, idx);
-      if (row)
-        acc += coef[idx] * row[j];
-      else if (bk == j)
-        acc += coef[idx] * v_is[bk];
+  double* const scr = c.scratch;
+  _Pragma("unroll 1") for (int g0 = 0; g0 < n; g0 += 256) {
+    double acc[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) acc[cc] = 0.0;
+    _Pragma("unroll 1") for (int rb = r0 + warp; rb < r1; rb += 2 * NW) {
+      const double* rowp[2];
+      int bk[2], idx[2];
+      double cf[2];
+      double v[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int r = rb + u * NW;
+        rowp[u] = nullptr;
+        bk[u] = -1;
+        idx[u] = -1;
+        cf[u] = 0.0;
+        if (r < r1) {
+          rowp[u] = get_row(c, rs, r, bk[u], idx[u]);
+          cf[u] = coef[idx[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const int j = g0 + lane + 32 * cc;
+          v[u][cc] = (rowp[u] && j < n) ? rowp[u][j] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (idx[u] >= 0) {
+          if (bk[u] < 0) {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) acc[cc] = fma(cf[u], v[u][cc], acc[cc]);
+          } else { // box row i_s[k] e_k
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              if (bk[u] == g0 + lane + 32 * cc) acc[cc] = fma(cf[u], v_is[bk[u]], acc[cc]);
+            }
+          }
+        }
+      }
     }
-    out[j] = (add ? add[j] : 0.0) + sign * acc;
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const int j = g0 + lane + 32 * cc;
+      if (j < n) scr[(size_t)warp * n + j] = acc[cc];
+    }
+  }
+  __syncthreads();
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sacc += scr[(size_t)w * n + j];
+    out[j] = (add ? add[j] : 0.0) + sign * sacc;
   }
   __syncthreads();
 }
@@ -890,7 +997,7 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu)
 
 // Remove dual slot k (k >= ne): Schur complement of the explicit inverse,
 //   S'^-1 = T - q q^T / T_kk   (T = S^-1 without row/column k, q = column k),
-// then in-place compaction. Replaces Ldlt::delete_at (ldlt.hpp:340-387).
+// then the last slot takes the place of k. Replaces Ldlt::delete_at (ldlt.hpp:340-387).
 __device__ __noinline__ void delete_slot(Ctx& c, int k)
 {
   PQP_VECS(c);
@@ -907,44 +1014,33 @@ __device__ __noinline__ void delete_slot(Ctx& c, int k)
   }
   __syncthreads();
   sym_rank1(T, v_s2, v_s3, ns, -1, 0.0);
-  // compaction: drop row k and column k (order preserving, in place)
-  const int e0 = sym_off(k + 1), e1 = sym_off(ns);
-  for (int eb = e0; eb < e1; eb += NT) {
-    const int e = eb + threadIdx.x;
-    double v = 0;
-    int row = 0, col = 0;
-    const bool valid = e < e1;
-    if (valid) {
-      row = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-      while (sym_off(row) > e) --row;
-      while (sym_off(row + 1) <= e) ++row;
-      col = e - sym_off(row);
-      v = T[e];
+  // drop row / column k: the LAST slot takes the freed position (slot order carries no meaning; the first version
+  // compacted the packed triangle in place, order preserving: O(ns^2) element moves behind two barriers per 256
+  // elements - the dominant cost of a deletion for the large shapes)
+  const int L = ns - 1;
+  if (k != L) {
+    const double* rowL = T + sym_off(L);
+    _Pragma("unroll 1") for (int i = threadIdx.x; i <= L; i += NT) v_s1[i] = rowL[i];
+    __syncthreads();
+    _Pragma("unroll 1") for (int i = threadIdx.x; i < L; i += NT) {
+      if (i == k)
+        T[sym_off(k) + k] = v_s1[L];
+      else if (i > k)
+        T[sym_off(i) + k] = v_s1[i];
+      else
+        T[sym_off(k) + i] = v_s1[i];
     }
-    __syncthreads();
-    if (valid && col != k) T[sym_off(row - 1) + col - (col > k ? 1 : 0)] = v;
-    __syncthreads();
   }
-  {
-    const int cons_k = c.slot_cons[k];
-    for (int i0 = k; i0 < ns - 1; i0 += NT) {
-      const int i = i0 + threadIdx.x;
-      const bool valid = i < ns - 1;
-      int scn = 0;
-      if (valid) scn = c.slot_cons[i + 1];
-      __syncthreads();
-      if (valid) {
-        c.slot_cons[i] = scn;
-        c.cons_slot[scn] = i;
-      }
-      __syncthreads();
+  if (threadIdx.x == 0) {
+    const int cons_k = c.slot_cons[k], cons_L = c.slot_cons[L];
+    if (k != L) {
+      c.slot_cons[k] = cons_L;
+      c.cons_slot[cons_L] = k;
     }
-    if (threadIdx.x == 0) {
-      c.cons_slot[cons_k] = -1;
-      c.ns = ns - 1;
-    }
-    __syncthreads();
+    c.cons_slot[cons_k] = -1;
+    c.ns = L;
   }
+  __syncthreads();
 }
 
 // S^-1 from the cached Gram matrix with the given proximal parameters

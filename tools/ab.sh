@@ -4,6 +4,6 @@
 reps=${1:-3}
 for i in $(seq $reps); do
   for v in base b200; do
-    PQP_B200_LIB=$PWD/proxsuite_b200/libpqp_$v.so timeout 200 python tools/gpu_check.py perf 2>&1 | grep -o "qps_per_s_dev[^,]*" | sed "s/^/$v /"
+    PQP_B200_LIB=$PWD/proxsuite_b200/libpqp_$v.so timeout 200 python tools/gpu_check.py perf 2>&1 | grep -o "t_solve_wall_s[^,]*\|solve_ms_dev[^,]*" | tr '\n' ' ' | sed "s/^/$v /"; echo
   done
 done

@@ -43,6 +43,12 @@ def run(name, kind, B, n, ne, ni, box=False, hessian=None, sparsity=0.15):
     print(f"{name}: B={B} n={n} n_eq={ne} n_in={ni} box={box} solved {int((r['info']['status'] == 0).sum())}/{B} pri {pri:.2e} dua {np.abs(dua).max():.2e} "
           f"iter {r['info']['iter'].mean():.1f} kernel {db.timings()['solve_ms']:.2f} ms -> {B / (db.timings()['solve_ms'] * 1e-3):.0f} QP/s (wall {dt * 1e3:.1f} ms) "
           f"smem {cfg['smem_bytes']} si_cap {cfg['si_cap']} retries {cfg['overflow_retries']}", flush=True)
+    if os.environ.get("PQP_PROFILE"):
+        pr = db.profile()
+        if pr:
+            tot = max(pr["total"], 1)
+            print("   cycles/QP:", {k: round(v / (2 * B)) for k, v in pr.items()}, flush=True)  # two solves since the batch was created
+            print("   share    :", {k: round(v / tot, 3) for k, v in pr.items()}, flush=True)
 
 
 if __name__ == "__main__":

@@ -115,7 +115,7 @@ if __name__ == "__main__":
             print("cycles per QP:", {k: round(v / 1024) for k, v in pr.items()})
             print("share:", {k: round(v / tot, 3) for k, v in pr.items()})
         if which in ("all", "perf"):
-            run_case("cfg2_1024", "strongly_convex", 1024, 100, 50, 100, compare=False, reps=3)
+            run_case("cfg2_%d" % int(os.environ.get("PERF_B", "1024")), "strongly_convex", int(os.environ.get("PERF_B", "1024")), 100, 50, 100, compare=False, reps=3)
     finally:
         with open(os.path.join(ROOT, "gpurun_out", "gpu_check.json"), "w") as f:
             json.dump(out, f, indent=1)
