@@ -235,6 +235,27 @@ int pqp_batch_timings(const pqp_batch* b, double* setup_ms, double* solve_ms, in
 int pqp_random_qp(int kind, uint64_t seed, int64_t dim, int64_t n_eq, int64_t n_in, double sparsity_factor, double strong_convexity_factor, double* H, double* g, double* A, double* b_, double* C, double* u, double* l, double* u_box,
                   double* l_box);
 
+/* ---- One batch sharded over several GPUs of one node -------------------------------------------------------------
+ * solve_in_parallel has no cross-QP state (parallel/qp_solve.hpp:55-59): a batch shards into contiguous slices
+ * [k B / G, (k + 1) B / G), one pqp_batch per listed device, no cross-device dependency inside the iteration; the
+ * only data movement is the scatter of the inputs (each device receives its own slice from the caller's host
+ * buffers) and the gather of the solutions into the caller's buffers. `devices` lists CUDA ordinals (an ordinal may
+ * be listed more than once). All calls address the WHOLE batch with host pointers laid out like pqp_batch_init's. */
+typedef struct pqp_sharded pqp_sharded;
+pqp_sharded* pqp_sharded_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box_constraints, int hessian_type, int dense_backend, const int* devices, int n_devices);
+void pqp_sharded_destroy(pqp_sharded* s);
+int pqp_sharded_count(const pqp_sharded* s);
+/* shard k: its per-device batch (for every pqp_batch_* call, e.g. the device-pointer entry points) and its slice */
+pqp_batch* pqp_sharded_shard(pqp_sharded* s, int k, int64_t* first, int64_t* count);
+int pqp_sharded_settings_set(pqp_sharded* s, const pqp_settings* in); /* every QP */
+int pqp_sharded_init(pqp_sharded* s, const double* H, const double* g, const double* A, const double* b_, const double* C, const double* l, const double* u, const double* l_box, const double* u_box, int compute_preconditioner,
+                     const double* rho, const double* mu_eq, const double* mu_in, const double* manual_minimal_H_eigenvalue);
+int pqp_sharded_update(pqp_sharded* s, const double* H, const double* g, const double* A, const double* b_, const double* C, const double* l, const double* u, const double* l_box, const double* u_box, int update_preconditioner,
+                       const double* rho, const double* mu_eq, const double* mu_in, const double* manual_minimal_H_eigenvalue);
+/* solve_in_parallel over all devices: every shard is enqueued first, then all are synchronised. */
+int pqp_sharded_solve(pqp_sharded* s);
+int pqp_sharded_results(pqp_sharded* s, double* x, double* y, double* z, double* se, double* si, pqp_info* info);
+
 const char* pqp_last_error(void);
 const char* pqp_version(void);
 

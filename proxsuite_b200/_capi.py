@@ -57,6 +57,8 @@ EXPORTED_SYMBOLS = [
     "pqp_batch_update", "pqp_batch_warm_start", "pqp_batch_solve", "pqp_batch_solve_async", "pqp_batch_sync",
     "pqp_batch_results", "pqp_batch_results_device", "pqp_batch_scaled", "pqp_batch_backward", "pqp_batch_backward_device", "pqp_batch_results_copy_device", "pqp_batch_cleanup", "pqp_batch_timings",
     "pqp_random_qp", "pqp_last_error", "pqp_version",
+    "pqp_sharded_create", "pqp_sharded_destroy", "pqp_sharded_count", "pqp_sharded_shard", "pqp_sharded_settings_set",
+    "pqp_sharded_init", "pqp_sharded_update", "pqp_sharded_solve", "pqp_sharded_results",
 ]
 
 _lib = None
@@ -107,6 +109,18 @@ def lib():
     L.pqp_batch_launch_config.argtypes = [vp, vp, vp, vp, vp]
     L.pqp_batch_profile.argtypes = [vp, vp, C.c_int]
     L.pqp_random_qp.argtypes = [C.c_int, C.c_uint64, i64, i64, i64, dbl, dbl] + [vp] * 9
+    L.pqp_sharded_create.restype = vp
+    L.pqp_sharded_create.argtypes = [i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+    L.pqp_sharded_destroy.argtypes = [vp]
+    L.pqp_sharded_destroy.restype = None
+    L.pqp_sharded_count.argtypes = [vp]
+    L.pqp_sharded_shard.restype = vp
+    L.pqp_sharded_shard.argtypes = [vp, C.c_int, vp, vp]
+    L.pqp_sharded_settings_set.argtypes = [vp, C.POINTER(pqp_settings)]
+    L.pqp_sharded_init.argtypes = [vp] + data + [C.c_int] + [vp] * 4
+    L.pqp_sharded_update.argtypes = [vp] + data + [C.c_int] + [vp] * 4
+    L.pqp_sharded_solve.argtypes = [vp]
+    L.pqp_sharded_results.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -615,6 +615,84 @@ class DenseBatch:
         return out[:k].reshape(-1, 6)
 
 
+class ShardedBatch:
+    """One batch of B same-shaped QPs sharded over several GPUs of this node from ONE process (pqp_sharded_* of the
+    C-ABI): contiguous slices, one device batch each, no cross-device dependency inside the iteration
+    (parallel/qp_solve.hpp:55-59). `devices`: CUDA ordinals (default: every visible device). The torch.distributed
+    variant (one process per GPU, NCCL gather of the solutions) is proxsuite_b200.sharding."""
+
+    def __init__(self, batch, n, n_eq, n_in, box_constraints=False, hessian_type=HessianType.Dense,
+                 dense_backend=DenseBackend.PrimalDualLDLT, devices=None):
+        self.lib = _capi.lib()
+        if devices is None:
+            import torch
+
+            devices = list(range(max(1, torch.cuda.device_count())))
+        self.devices = [int(d) for d in devices]
+        arr = (ct.c_int * len(self.devices))(*self.devices)
+        self.batch, self.n, self.n_eq, self.n_in, self.box = int(batch), int(n), int(n_eq), int(n_in), bool(box_constraints)
+        self.nc = self.n_in + (self.n if self.box else 0)
+        self.handle = self.lib.pqp_sharded_create(self.batch, self.n, self.n_eq, self.n_in, int(self.box), int(hessian_type), int(dense_backend), arr, len(self.devices))
+        if not self.handle:
+            msg = _capi.last_error()
+            raise (ValueError if "wrong argument" in msg else RuntimeError)(f"proxsuite_b200: cannot create sharded batch: {msg}")
+        self.settings = Settings(DenseBackend(self.lib.pqp_dense_backend_choice(int(dense_backend), self.n, self.n_eq, self.n_in, int(self.box))))
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self.lib.pqp_sharded_destroy(h)
+            self.handle = None
+
+    def shards(self):
+        """[(device, first, count)] of the slices"""
+        out = []
+        for k in range(self.lib.pqp_sharded_count(self.handle)):
+            f, c = ct.c_int64(0), ct.c_int64(0)
+            self.lib.pqp_sharded_shard(self.handle, k, ct.byref(f), ct.byref(c))
+            out.append((self.devices[k], f.value, c.value))
+        return out
+
+    def _feed(self, fn, flag, H, g, A, b, C, l, u, l_box, u_box, rho, mu_eq, mu_in, eig):
+        B, n, ne, ni = self.batch, self.n, self.n_eq, self.n_in
+
+        def chk(a, shape, what):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+            if a.size == 0:
+                return None
+            if a.size != int(np.prod(shape)):
+                raise ValueError(f"wrong argument size: expected {shape} for {what}, got {a.shape}")
+            return a
+        arrs = [chk(H, (B, n, n), "H"), chk(g, (B, n), "g"), chk(A, (B, ne, n), "A"), chk(b, (B, ne), "b"), chk(C, (B, ni, n), "C"),
+                chk(l, (B, ni), "l"), chk(u, (B, ni), "u"), chk(l_box, (B, n), "l_box"), chk(u_box, (B, n), "u_box")]
+        keep = [_opt_scalar(v) for v in (rho, mu_eq, mu_in, eig)]
+        _capi.check(self.lib.pqp_sharded_settings_set(self.handle, ct.byref(self.settings._c)))
+        _capi.check(fn(self.handle, *[_ptr(a) for a in arrs], int(flag), *[k[1] for k in keep]))
+
+    def init(self, H=None, g=None, A=None, b=None, C=None, l=None, u=None, l_box=None, u_box=None, compute_preconditioner=True,
+             rho=None, mu_eq=None, mu_in=None, manual_minimal_H_eigenvalue=None):
+        self._feed(self.lib.pqp_sharded_init, compute_preconditioner, H, g, A, b, C, l, u, l_box, u_box, rho, mu_eq, mu_in, manual_minimal_H_eigenvalue)
+
+    def update(self, H=None, g=None, A=None, b=None, C=None, l=None, u=None, l_box=None, u_box=None, update_preconditioner=False,
+               rho=None, mu_eq=None, mu_in=None, manual_minimal_H_eigenvalue=None):
+        self._feed(self.lib.pqp_sharded_update, update_preconditioner, H, g, A, b, C, l, u, l_box, u_box, rho, mu_eq, mu_in, manual_minimal_H_eigenvalue)
+
+    def solve(self):
+        _capi.check(self.lib.pqp_sharded_settings_set(self.handle, ct.byref(self.settings._c)))
+        _capi.check(self.lib.pqp_sharded_solve(self.handle))
+
+    def results(self):
+        B = self.batch
+        x, y, z = np.zeros((B, self.n)), np.zeros((B, self.n_eq)), np.zeros((B, self.nc))
+        se, si = np.zeros((B, self.n_eq)), np.zeros((B, self.nc))
+        info = (_capi.pqp_info * B)()
+        _capi.check(self.lib.pqp_sharded_results(self.handle, _ptr(x), _ptr(y), _ptr(z), _ptr(se), _ptr(si), info))
+        rec = np.frombuffer(info, dtype=_capi.INFO_DTYPE, count=B)
+        return dict(x=x, y=y, z=z, se=se, si=si, info={k: np.ascontiguousarray(rec[k]) for k in rec.dtype.names})
+
+
 _GEN_KINDS = {"strongly_convex": 0, "not_strongly_convex": 1, "degenerate": 2, "box_constrained": 3,
               "box_benchmark": 4, "diagonal_benchmark": 5}
 

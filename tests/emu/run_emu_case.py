@@ -241,7 +241,43 @@ def qplayer_device_api_case():
         os.environ.pop("PQP_QPLAYER_DEVICE_API", None)
 
 
+def qplayer_infeas_case():
+    """QPFunction(structural_feasibility=False) (QPFunctionFn_infeas, qplayer.py:255-610): the body of the GPU test"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("tq", os.path.join(ROOT, "tests", "test_gpu_qplayer_backward.py"))
+    tq = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tq)
+    try:
+        tq.test_torch_qp_layer_closest_feasible_variant(proxqp, O)
+        ok = True
+    except AssertionError as e:
+        print("qplayer_infeas failed:", e, flush=True)
+        ok = False
+    print(json.dumps(dict(name="qplayer_infeas", ok=ok)), flush=True)
+    return ok
+
+
+def sharded_case():
+    """pqp_sharded_* behind the C-ABI: shards on the emulated device must reproduce one DenseBatch bit for bit"""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("tb", os.path.join(ROOT, "tests", "test_gpu_baseline_configs.py"))
+    tb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tb)
+    torch.cuda.device_count = lambda: 1
+    try:
+        tb.test_sharded_batch_behind_the_c_abi(proxqp, O)
+        ok = True
+    except AssertionError as e:
+        print("sharded failed:", e, flush=True)
+        ok = False
+    print(json.dumps(dict(name="sharded", ok=ok)), flush=True)
+    return ok
+
+
 CASES = {
+    "qplayer_infeas": qplayer_infeas_case,
+    "sharded": sharded_case,
     "qplayer": qplayer_case,
     "qplayer_device_api": qplayer_device_api_case,
     "closest_feasible": closest_feasible_case,

@@ -57,7 +57,12 @@ def test_qplayer_backward_on_the_emulator(emu_lib):
 def test_torch_qp_layer_gradients_on_the_emulator(emu_lib):
     """proxsuite_b200.torch.QPFunction (mirror of proxsuite.torch.qplayer.QPFunction): autograd gradients w.r.t.
     H, g, A, b, C, u against central finite differences through the layer's forward pass."""
-    run_cases(emu_lib, ["qplayer", "qplayer_device_api"])
+    run_cases(emu_lib, ["qplayer", "qplayer_device_api", "qplayer_infeas"])
+
+
+def test_sharded_batch_of_the_c_abi_on_the_emulator(emu_lib):
+    """pqp_sharded_* (include/pqp.h): uneven slices over a device list, bit-identical to one batch; update + re-solve."""
+    run_cases(emu_lib, ["sharded"])
 
 
 @pytest.mark.parametrize("order", ["reverse", "stride"])

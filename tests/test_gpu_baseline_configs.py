@@ -212,3 +212,46 @@ def test_closest_feasible_mode(px, oracle):
         assert int(r.info.status) in ok_states and ro.info.status in ok_states
         assert np.abs(r.x - ro.x).max() <= XTOL * max(1.0, np.abs(ro.x).max())
         assert np.abs(r.si - ro.si).max() <= XTOL and (dims[1] == 0 or np.abs(r.se - ro.se).max() <= XTOL)
+
+
+def test_sharded_batch_behind_the_c_abi(px, oracle):
+    """pqp_sharded_* (include/pqp.h): one batch sharded over a device list from ONE process. With every visible GPU
+    (and, on a one-GPU box, the same ordinal listed twice) the results must be bit-identical to one DenseBatch:
+    QPs are independent (parallel/qp_solve.hpp:55-59), the slice a QP lands in must not matter."""
+    import torch
+
+    B, n, ne, ni = 37, 30, 10, 20  # odd batch: uneven slices
+    data = [oracle.generate_qp("strongly_convex", i, n, ne, ni) for i in range(B)]
+    st = {k: np.stack([d[k] for d in data]) for k in KEYS}
+    ref = px.dense.DenseBatch(B, n, ne, ni)
+    ref.settings.eps_abs = EPS
+    ref.settings.eps_rel = 0
+    ref.init(**st)
+    ref.solve()
+    r0 = ref.results()
+    ndev = torch.cuda.device_count()
+    for devices in ([0, 0, 0], list(range(ndev)) if ndev > 1 else [0, 0]):
+        sb = px.dense.ShardedBatch(B, n, ne, ni, devices=devices)
+        sb.settings.eps_abs = EPS
+        sb.settings.eps_rel = 0
+        sb.init(**st)
+        sb.solve()
+        r = sb.results()
+        sl = sb.shards()
+        assert sum(c for _, _, c in sl) == B and [f for _, f, _ in sl] == sorted(f for _, f, _ in sl)
+        assert (r["info"]["status"] == 0).all()
+        for k in ("x", "y", "z"):
+            assert np.array_equal(r[k], r0[k]), (devices, k)
+        assert np.array_equal(r["info"]["iter"], r0["info"]["iter"])
+        # update of g on the whole sharded batch, then a second solve
+        sb.update(g=st["g"] * 1.25)
+        sb.solve()
+        r2 = sb.results()
+        ref2 = px.dense.DenseBatch(B, n, ne, ni)
+        ref2.settings.eps_abs = EPS
+        ref2.settings.eps_rel = 0
+        ref2.init(**st)
+        ref2.solve()
+        ref2.update(g=st["g"] * 1.25)
+        ref2.solve()
+        assert np.array_equal(r2["x"], ref2.results()["x"])

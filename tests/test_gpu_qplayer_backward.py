@@ -139,3 +139,73 @@ def test_torch_qp_layer_on_cuda_tensors(px):
             fd = float((loss_of(plus) - loss_of(minus)) / (2 * t))
         an = float((T[k].grad * dvt).sum())
         assert abs(fd - an) <= 5e-4 * max(1.0, abs(fd)), (k, fd, an)
+
+
+def _infeas_layer_problem(rng, nb, nz, neq, nin, infeasible):
+    L = rng.standard_normal((nb, nz, nz))
+    Q = np.einsum("bij,bkj->bik", L, L) + 0.5 * np.eye(nz)
+    p = rng.standard_normal((nb, nz))
+    A = rng.standard_normal((nb, neq, nz))
+    xs = rng.standard_normal((nb, nz))
+    b = np.einsum("bij,bj->bi", A, xs)
+    G = rng.standard_normal((nb, nin, nz))
+    gx = np.einsum("bij,bj->bi", G, xs)
+    l = gx - rng.uniform(0.05, 0.4, (nb, nin))
+    u = gx + rng.uniform(0.05, 0.4, (nb, nin))
+    if infeasible:  # two parallel inequality rows that cannot both hold
+        G[:, 1] = G[:, 0]
+        l[:, 1] = u[:, 0] + 1.0
+        u[:, 1] = u[:, 0] + 2.0
+    return dict(Q=Q, p=p, A=A, b=b, G=G, l=l, u=u)
+
+
+def test_torch_qp_layer_closest_feasible_variant(px, oracle):
+    """QPFunction(structural_feasibility=False) == the reference's QPFunctionFn_infeas (qplayer.py:255-610).
+    (a) On feasible QPs its outputs and gradients equal the feasible layer's and central finite differences.
+    (b) On infeasible QPs the forward pass returns the oracle's closest-feasible solution (primal_infeasibility_solving
+    on the single-sided QP) with non-zero slacks s_i, and the gradients match finite differences through the layer."""
+    import torch
+
+    from proxsuite_b200.torch import QPFunction
+
+    rng = np.random.default_rng(1)
+    nb, nz, neq, nin = 2, 6, 2, 3
+    keys = ("Q", "p", "A", "b", "G", "l", "u")
+    for infeasible in (False, True):
+        d = _infeas_layer_problem(rng, nb, nz, neq, nin, infeasible)
+        T = {k: torch.tensor(d[k], dtype=torch.float64, requires_grad=True) for k in keys}
+        w = torch.tensor(rng.standard_normal((nb, nz)))
+        layer = QPFunction(eps=1e-10, maxIter=60 if infeasible else 200, eps_backward=1e-10, structural_feasibility=False)
+
+        def loss_of(t):
+            z, lam, nu, se, si = layer(*[t[k] for k in keys])
+            assert z.shape == (nb, nz) and lam.shape == (nb, neq) and nu.shape == (nb, nin) and se.shape == (nb, neq) and si.shape == (nb, nin)
+            return (w * z).sum(), z, si
+
+        loss, z, si = loss_of(T)
+        loss.backward()
+        if not infeasible:
+            T2 = {k: v.detach().clone().requires_grad_(True) for k, v in T.items()}
+            z2, _, _ = QPFunction(eps=1e-10, maxIter=200, eps_backward=1e-10)(*[T2[k] for k in keys])
+            (w * z2).sum().backward()
+            assert float((z - z2).abs().max()) <= 1e-7 and float(si.abs().max()) <= 1e-7
+            for k in keys:
+                assert float((T[k].grad - T2[k].grad).abs().max()) <= 1e-4 * max(1.0, float(T2[k].grad.abs().max())), k
+        else:
+            assert float(si.abs().max()) > 0.1  # the QP is infeasible: the shifted constraints are what is solved
+            for i in range(nb):  # forward parity with the oracle on the single-sided QP
+                G2 = np.concatenate((-d["G"][i], d["G"][i]))
+                h = np.concatenate((-d["l"][i], d["u"][i]))
+                qo = oracle.OracleQP(nz, neq, 2 * nin)
+                qo.set(eps_abs=1e-10, eps_rel=0, primal_infeasibility_solving=1, max_iter=60, max_iter_in=100, default_rho=5e-5, refactor_rho_threshold=5e-5)
+                qo.init(H=d["Q"][i], g=d["p"][i], A=d["A"][i], b=d["b"][i], C=G2, l=np.full(2 * nin, -1e20), u=h, rho=5e-5)
+                ro = qo.solve()
+                assert np.abs(z[i].detach().numpy() - ro.x).max() <= 1e-6 * max(1.0, np.abs(ro.x).max())
+        t = 1e-6
+        for k in ("p", "b", "u") + (("G", "l") if not infeasible else ()):
+            dv = torch.tensor(rng.standard_normal(tuple(T[k].shape)))
+            plus = {kk: (T[kk].detach() + t * dv if kk == k else T[kk].detach()) for kk in keys}
+            minus = {kk: (T[kk].detach() - t * dv if kk == k else T[kk].detach()) for kk in keys}
+            fd = float((loss_of(plus)[0] - loss_of(minus)[0]) / (2 * t))
+            an = float((T[k].grad * dv).sum())
+            assert abs(fd - an) <= 2e-3 * max(1.0, abs(fd)), (infeasible, k, fd, an)
