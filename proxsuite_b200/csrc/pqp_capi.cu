@@ -330,6 +330,86 @@ fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_ca
   return (L.in_smem[PA_VEC] && L.in_smem[PA_MS] && (!pi_smem || L.in_smem[PA_M1])) ? 0 : 1;
 }
 
+// Big layout (kind 2) of the BIG variant of the tile body (pqp_kernels.cu, namespace bigk): pass scratch, reduction
+// scratch and the two coefficient vectors in shared memory (absolute offsets in voff), then the vector arena if it
+// fits (else in the workspace); packed S^-1 (order max(n, capacity): P is inverted there as well), P^-1 (n x ldn),
+// Bt, W (n x ldb) and G (m x ldb) in the per-CTA global workspace. No capacity limit, no overflow retries.
+int
+fill_layout_big(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int ctas)
+{
+  std::memset(&L, 0, sizeof(L));
+  const int n = d.n, ne = d.ne, nc = d.nc, cap = d.cap;
+  auto rnd = [](int64_t v) { return (v + 1) & ~int64_t(1); };
+  const int m = ne + nc, sc = cap + 2;
+  int vsz[V_COUNT];
+  for (int& v : vsz) v = 0;
+  vsz[V_X] = n; vsz[V_Y] = ne; vsz[V_Z] = nc; vsz[V_XP] = n; vsz[V_YP] = ne; vsz[V_ZP] = nc;
+  vsz[V_DX] = n; vsz[V_DS] = sc; vsz[V_DZ] = nc;
+  vsz[V_RX] = n; vsz[V_RS] = sc; vsz[V_EX] = n; vsz[V_ES] = sc;
+  vsz[V_DUAL] = n; vsz[V_SE] = m + 2; vsz[V_RUP] = 0; vsz[V_SI] = nc;
+  vsz[V_HDX] = n; vsz[V_ADX] = m + 2; vsz[V_ATDY] = n; vsz[V_CDX] = 0; vsz[V_CTDZ] = n; vsz[V_Q] = n;
+  vsz[V_GS] = n; vsz[V_BS] = ne; vsz[V_US] = nc; vsz[V_LS] = nc; vsz[V_IS] = d.box ? n : 2; vsz[V_DELTA] = n + ne + nc;
+  vsz[V_B] = ne; vsz[V_U] = nc; vsz[V_L] = nc;
+  vsz[V_D1INV] = (d.hess == PQP_HESSIAN_DENSE) ? 2 : n; vsz[V_DSV] = 2; vsz[V_DSINV] = 2;
+  vsz[V_T1] = n; vsz[V_T2] = n; vsz[V_T3] = n;
+  vsz[V_S1] = sc; vsz[V_S2] = sc; vsz[V_S3] = sc; vsz[V_S4] = 0;
+  vsz[V_ALPHAS] = 2 * nc + 2; vsz[V_GRADS] = 4;
+  // shared-memory part (absolute offsets)
+  const int ord = std::max(n, cap);
+  const int uv_ld = (ord + 2) & ~1;
+  const int scratch = std::max(8 * uv_ld, PQP_NW * (std::max(ord, m) + 2));
+  int64_t sm = 0;
+  L.voff[V_SCRATCH] = (int32_t)sm; sm += rnd(scratch);
+  L.voff[V_RED] = (int32_t)sm;     sm += rnd(PQP_NW * 16);
+  L.voff[V_KT] = (int32_t)sm;      sm += rnd(m + 4);
+  L.voff[V_KT2] = (int32_t)sm;     sm += rnd(m + 4);
+  L.scratch_doubles = scratch;
+  // vector arena (relative offsets)
+  int off = 0;
+  for (int v = 0; v < V_COUNT; ++v) {
+    if (v == V_SCRATCH || v == V_RED || v == V_KT || v == V_KT2) continue;
+    L.voff[v] = off;
+    off += (int)rnd(vsz[v]);
+  }
+  L.voff[V_S4] = L.voff[V_S3];
+  L.voff[V_RUP] = L.voff[V_SE] + ne;
+  L.voff[V_CDX] = L.voff[V_ADX] + ne;
+  L.vec_doubles = off;
+  L.si_cap = cap;
+  L.ctas_per_sm = ctas;
+  L.kind = 2;
+  const int ldn = (n + 1) & ~1, ldb = (m + 1) & ~1;
+  int64_t sz[PA_COUNT];
+  sz[PA_M1] = (d.hess == PQP_HESSIAN_DENSE) ? rnd((int64_t)n * ldn + 4) : 2;
+  sz[PA_AS] = rnd((int64_t)n * ldb + 4);                 // Bt
+  sz[PA_MS] = rnd((int64_t)ord * (ord + 1) / 2 + 4);     // packed S^-1 (and P during its inversion)
+  sz[PA_G] = rnd((int64_t)m * ldb + 4);                  // G, full square (lower block triangle used)
+  sz[PA_Y] = rnd((int64_t)n * ldb + 4);                  // W
+  sz[PA_VEC] = L.vec_doubles;
+  const int64_t nlist = std::max(nc, cap);
+  L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);
+  const int64_t budget = budget_bytes - 1024 /*static shared memory*/ - L.smem_int_bytes;
+  if (sm * 8 > budget) return 1; // not even the scratch fits
+  int64_t smem_d = sm, ws_d = 0;
+  if ((smem_d + sz[PA_VEC]) * 8 <= budget) {
+    L.in_smem[PA_VEC] = 1;
+    L.off[PA_VEC] = smem_d;
+    smem_d += sz[PA_VEC];
+  } else {
+    L.in_smem[PA_VEC] = 0;
+    L.off[PA_VEC] = ws_d;
+    ws_d += sz[PA_VEC];
+  }
+  for (int id : { (int)PA_MS, (int)PA_M1, (int)PA_AS, (int)PA_G, (int)PA_Y }) {
+    L.in_smem[id] = 0;
+    L.off[id] = ws_d;
+    ws_d += sz[id];
+  }
+  L.smem_doubles = (int32_t)smem_d;
+  L.ws_doubles = std::max<int64_t>(ws_d, 2);
+  return 0;
+}
+
 int64_t
 sym_doubles(int64_t m)
 {
@@ -388,6 +468,21 @@ make_layout(pqp_batch* b)
           break;
         }
       }
+    }
+  }
+  // big layout (BIG variant of the tile body): everything the tile kernel proper cannot hold, n even
+  if (!done && (m == "auto" || m == "big") && (d.n % 2) == 0 && d.n >= 2 && d.nc > 0 && !std::getenv("PQP_NO_BIG")) {
+    const int64_t half = ((int64_t)smem_sm - 2 * 1024) / 2;
+    PqpLayout two, one;
+    const int r2 = fill_layout_big(d, two, half, 2);           // 0: the shared-memory scratch part fits twice per SM
+    const int r1 = fill_layout_big(d, one, (int64_t)max_smem, 1);
+    // two CTAs per SM when the vector arena fits in half an SM as well - or when it would not fit in a whole one either
+    if (r2 == 0 && (two.in_smem[PA_VEC] || r1 != 0 || !one.in_smem[PA_VEC])) {
+      b->lay = two;
+      done = true;
+    } else if (r1 == 0) {
+      b->lay = one;
+      done = true;
     }
   }
   if (!done && (m == "auto" || m == "compact")) {

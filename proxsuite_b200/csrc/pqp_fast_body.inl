@@ -337,8 +337,85 @@ __device__ void axpy_pass_t(const Ctx& c, const double* __restrict__ base0, int 
   __syncthreads();
 }
 
+#ifdef PQP_BIG
+// BIG variant (any number of columns): the same pass, columns handled in groups of 256 (register accumulators for
+// one group at a time), rows predicated instead of peeled. Partial vectors: c.scratch, NW x 2*np doubles.
+__device__ __noinline__ void axpy_pass_big(const Ctx& c, const double* __restrict__ base0, int split, const double* __restrict__ base1, int ld, const int* __restrict__ list, int byid, int nrows, const double* __restrict__ coef, int ncols, double* out, const double* add, double sign, double* raw)
+{
+  constexpr int NCH = 4, UNR = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* const scr = c.scratch;
+  const int np = (ncols + 1) >> 1;
+  double2* const scr2 = reinterpret_cast<double2*>(scr);
+  _Pragma("unroll 1") for (int g0 = 0; g0 < np; g0 += 32 * NCH) {
+    bool pv[NCH];
+    double2 acc[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      pv[ch] = g0 + lane + 32 * ch < np;
+      acc[ch] = make_double2(0.0, 0.0);
+    }
+    _Pragma("unroll 1") for (int k = warp; k < nrows; k += UNR * NW) {
+      const double2* rp[UNR];
+      double cf[UNR];
+      bool rv[UNR];
+      double2 v[UNR][NCH];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int kk = k + u * NW;
+        rv[u] = kk < nrows;
+        cf[u] = 0.0;
+        rp[u] = nullptr;
+        if (rv[u]) {
+          int id = kk;
+          const double* b = base0;
+          if (kk >= split) {
+            b = base1;
+            id = list ? list[kk] : kk - split;
+          }
+          cf[u] = coef[(byid && kk >= split) ? id : kk];
+          rp[u] = reinterpret_cast<const double2*>(b + (size_t)id * (size_t)ld) + g0 + lane;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) v[u][ch] = (rv[u] && pv[ch]) ? rp[u][32 * ch] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (rv[u]) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            acc[ch].x = fma(cf[u], v[u][ch].x, acc[ch].x);
+            acc[ch].y = fma(cf[u], v[u][ch].y, acc[ch].y);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      if (pv[ch]) scr2[warp * np + g0 + lane + 32 * ch] = acc[ch];
+    }
+  }
+  __syncthreads();
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < ncols; j += NT) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += scr[w * 2 * np + j];
+    out[j] = (add ? add[j] : 0.0) + sign * s;
+    if (raw) raw[j] = s;
+  }
+  __syncthreads();
+}
+#endif
+
 __device__ __noinline__ void axpy_pass2(const Ctx& c, const double* base0, int split, const double* base1, int ld, const int* list, int byid, int nrows, const double* coef, int ncols, double* out, const double* add, double sign, double* raw = nullptr)
 {
+#ifdef PQP_BIG
+  axpy_pass_big(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign, raw);
+  return;
+#endif
   const int np = (ncols + 1) >> 1;
   if (np <= 32)
     axpy_pass_t<1>(c, base0, split, base1, ld, list, byid, nrows, coef, ncols, out, add, sign, raw);
@@ -418,8 +495,68 @@ __device__ void bt_dot_t(const Ctx& c, const double* __restrict__ coef1, const d
   }
   __syncthreads();
 }
+#ifdef PQP_BIG
+// BIG variant: any row length; the coefficient vectors are re-read per 256-column group (shared memory) instead of
+// being held in registers for the whole pass.
+__device__ __noinline__ void bt_dot_big(const Ctx& c, const double* __restrict__ coef1, const double* __restrict__ coef2, double* out1, const double* add, double sign, double* raw1, double* out2)
+{
+  constexpr int NCH = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = c.n, np = c.ldb >> 1;
+  const bool two = coef2 != nullptr;
+  _Pragma("unroll 1") for (int jb = warp; jb < n; jb += 4 * NW) {
+    double d1[4] = { 0.0, 0.0, 0.0, 0.0 }, d2[4] = { 0.0, 0.0, 0.0, 0.0 };
+    _Pragma("unroll 1") for (int g0 = 0; g0 < np; g0 += 32 * NCH) {
+      bool pv[NCH];
+      double2 c1[NCH], c2[NCH];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        pv[ch] = g0 + lane + 32 * ch < np;
+        c1[ch] = pv[ch] ? reinterpret_cast<const double2*>(coef1)[g0 + lane + 32 * ch] : make_double2(0.0, 0.0);
+        c2[ch] = (two && pv[ch]) ? reinterpret_cast<const double2*>(coef2)[g0 + lane + 32 * ch] : make_double2(0.0, 0.0);
+      }
+      double2 v[4][NCH];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = jb + u * NW;
+        const double2* rp = reinterpret_cast<const double2*>(c.Bt + (size_t)(j < n ? j : 0) * c.ldb) + g0 + lane;
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) v[u][ch] = (j < n && pv[ch]) ? rp[32 * ch] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          d1[u] = fma(v[u][ch].x, c1[ch].x, d1[u]);
+          d1[u] = fma(v[u][ch].y, c1[ch].y, d1[u]);
+          if (two) {
+            d2[u] = fma(v[u][ch].x, c2[ch].x, d2[u]);
+            d2[u] = fma(v[u][ch].y, c2[ch].y, d2[u]);
+          }
+        }
+      }
+    }
+    reduce_rows<4>(d1, lane);
+    if (two) reduce_rows<4>(d2, lane);
+    if ((lane & 7) == 0) {
+      const int j = jb + (lane >> 3) * NW;
+      if (j < n) {
+        out1[j] = (add ? add[j] : 0.0) + sign * d1[0];
+        if (raw1) raw1[j] = d1[0];
+        if (two) out2[j] = d2[0];
+      }
+    }
+  }
+  __syncthreads();
+}
+#endif
+
 __device__ __noinline__ void bt_dot(const Ctx& c, const double* coef1, const double* coef2, double* out1, const double* add, double sign, double* raw1, double* out2)
 {
+#ifdef PQP_BIG
+  bt_dot_big(c, coef1, coef2, out1, add, sign, raw1, out2);
+  return;
+#endif
   const int np = c.ldb >> 1;
   if (coef2) {
     if (np <= 64)
@@ -500,6 +637,7 @@ __device__ __noinline__ void gemm_tn(const double* __restrict__ CM, int ldc, con
   __syncthreads();
 }
 
+#ifndef PQP_BIG
 // ---------------------------------------------------------------------------
 // Symmetric matrices in TILE storage (S^-1, and P during its inversion).
 // The lower triangle is cut into 32 x 32 tiles (bi, bj), bj <= bi, each stored
@@ -825,6 +963,243 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
   __syncthreads();
 }
 
+#else // PQP_BIG
+// ---------------------------------------------------------------------------
+// BIG variant: symmetric matrices (S^-1, and P during its inversion) as a PACKED lower triangle (row i holds the
+// columns 0..i) in the per-CTA global workspace (L2 / HBM), any order. Same interface as the tile storage above;
+// the primitives are loop based (no compile-time block count) and keep several independent loads in flight.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int ts_idx(int, int i, int j)
+{
+  return ((i * (i + 1)) >> 1) + j; // j <= i
+}
+__device__ __forceinline__ double ts_get(const double* T, int, int i, int j)
+{
+  return (i >= j) ? T[ts_idx(0, i, j)] : T[ts_idx(0, j, i)];
+}
+__device__ __forceinline__ void ts_put(double* T, int, int i, int j, double v)
+{
+  const int hi = i >= j ? i : j, lo = i >= j ? j : i;
+  T[ts_idx(0, hi, lo)] = v;
+}
+__device__ __forceinline__ int ts_extent(int, int n)
+{
+  return (n * (n + 1)) >> 1;
+}
+
+// y = T x (order n), x and y must not alias. Uses c.scratch (NW x n doubles).
+//   y_i = sum_{j <= i} T[i][j] x_j  (row part: a warp owns row i, coalesced loads, one warp reduction)
+//       + sum_{i' > i} T[i'][i] x_i' (column part, AXPY form: lane-stationary accumulators for a group of 256 columns)
+// Row i belongs to the same lane-0 thread in every column group (256 is a multiple of NW): fixed summation order.
+__device__ __noinline__ void tsym_mv(const Ctx& c, const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* const scr = c.scratch;
+  _Pragma("unroll 1") for (int g0 = 0; g0 < n; g0 += 256) {
+    double acc[8], xl[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const int j = g0 + lane + 32 * cc;
+      acc[cc] = 0.0;
+      xl[cc] = (j < n) ? x[j] : 0.0;
+    }
+    _Pragma("unroll 1") for (int i = g0 + warp; i < n; i += 2 * NW) { // two rows of the warp in flight
+      const int i2 = i + NW;
+      const bool r2 = i2 < n;
+      const double* row = T + ts_idx(0, i, 0);
+      const double* row2 = T + ts_idx(0, r2 ? i2 : i, 0);
+      const double xi = x[i], xi2 = r2 ? x[i2] : 0.0;
+      double a[8], b[8];
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const int j = g0 + lane + 32 * cc;
+        a[cc] = (j <= i) ? row[j] : 0.0;
+        b[cc] = (r2 && j <= i2) ? row2[j] : 0.0;
+      }
+      double d = 0.0, d2 = 0.0;
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const int j = g0 + lane + 32 * cc;
+        d = fma(a[cc], xl[cc], d);
+        d2 = fma(b[cc], xl[cc], d2);
+        if (j < i) acc[cc] = fma(a[cc], xi, acc[cc]);
+        if (r2 && j < i2) acc[cc] = fma(b[cc], xi2, acc[cc]);
+      }
+      d = warp_sum(d);
+      d2 = warp_sum(d2);
+      if (lane == 0) {
+        y[i] = (g0 == 0) ? d : y[i] + d;
+        if (r2) y[i2] = (g0 == 0) ? d2 : y[i2] + d2;
+      }
+    }
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) {
+      const int j = g0 + lane + 32 * cc;
+      if (j < n) scr[(size_t)warp * n + j] = acc[cc];
+    }
+  }
+  __syncthreads();
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
+    double sacc = y[j];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) sacc += scr[(size_t)w * n + j];
+    y[j] = sacc;
+  }
+  __syncthreads();
+}
+
+// T[i][j] += u_i v_j on the packed lower triangle (j <= i < n)
+__device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, const double* __restrict__ u, const double* __restrict__ v, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
+    double* row = T + ts_idx(0, i, 0);
+    const double ui = u[i];
+    _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 128) { // four independent read-modify-writes per lane
+      double a[4], vv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + 32 * q;
+        a[q] = (j <= i) ? row[j] : 0.0;
+        vv[q] = (j <= i) ? v[j] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + 32 * q;
+        if (j <= i) row[j] = fma(ui, vv[q], a[q]);
+      }
+    }
+  }
+  (void)c;
+  __syncthreads();
+}
+
+// T[i][j] += sum_{k<4} U_k[i] V_k[j] (j <= i < n), k = 0..3 in order; U_k = U + k ldv, V_k = V + k ldv
+__device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
+    double* row = T + ts_idx(0, i, 0);
+    const double u0 = U[i], u1 = U[ldv + i], u2 = U[2 * ldv + i], u3 = U[3 * ldv + i];
+    _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 64) {
+      double a[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int j = j0 + 32 * q;
+        a[q] = (j <= i) ? row[j] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int j = j0 + 32 * q;
+        if (j <= i) row[j] = fma(u3, V[3 * ldv + j], fma(u2, V[2 * ldv + j], fma(u1, V[ldv + j], fma(u0, V[j], a[q]))));
+      }
+    }
+  }
+  (void)c;
+  __syncthreads();
+}
+
+// In-place inverse of the SPD matrix in packed storage by blocked symmetric Gauss-Jordan sweeps (four pivots per
+// pass over the triangle; see the tile version above for the algebra). Any n: a thread sweeps the panel rows
+// i = tid, tid + NT, ... in registers (the 4 x 4 pivot block is swept redundantly by every thread). `uv`: 8 ldv
+// doubles. After all blocks the array holds -T^-1, negated at the end.
+__device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict__ T, double* __restrict__ uv, int ldv, int n)
+{
+  double* const U = uv;
+  double* const V = uv + 4 * ldv;
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    const int kb = min(4, n - k0);
+    double a0[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int bq = 0; bq < 4; ++bq) {
+        const int hi = k0 + (a > bq ? a : bq), lo = k0 + (a > bq ? bq : a);
+        a0[a][bq] = (a < kb && bq < kb) ? T[ts_idx(0, hi, lo)] : ((a == bq) ? 1.0 : 0.0);
+      }
+    }
+    __syncthreads(); // every thread holds the pivot block before anyone overwrites it
+    _Pragma("unroll 1") for (int i = threadIdx.x; i < n; i += NT) {
+      double a[4][4], p[4], ui[4], vi[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[q][r] = a0[q][r];
+      }
+      const int ai = i - k0; // position of this row inside the pivot block when 0 <= ai < kb
+      const bool inK = (ai >= 0) && (ai < kb);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int col = k0 + l;
+        double v = 0.0;
+        if (l < kb) {
+          if (inK) { // rows of the pivot block take their panel from the register copy (their entries are being overwritten)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (ai == q) v = a0[q][l];
+            }
+          } else {
+            v = (i >= col) ? T[ts_idx(0, i, col)] : T[ts_idx(0, col, i)];
+          }
+        }
+        p[l] = v;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < kb) {
+          const double inv = 1.0 / a[k][k];
+          double vK[4];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) vK[l] = -a[k][l] * inv;
+          const double pk = p[k];
+          if (ai == k) {
+            ui[k] = 0.0;
+            vi[k] = 0.0;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? -inv : p[l] * inv;
+          } else {
+            ui[k] = inK ? 0.0 : pk;
+            vi[k] = inK ? 0.0 : -pk * inv;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? pk * inv : fma(pk, vK[l], p[l]);
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (m != k) {
+              const double amk = a[m][k];
+#pragma unroll
+              for (int l = 0; l < 4; ++l) a[m][l] = (l == k) ? amk * inv : fma(amk, vK[l], a[m][l]);
+            }
+          }
+#pragma unroll
+          for (int l = 0; l < 4; ++l) a[k][l] = (l == k) ? -inv : a[k][l] * inv;
+        } else {
+          ui[k] = 0.0;
+          vi[k] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const int col = k0 + l;
+        if (l < kb) {
+          if (i >= col)
+            T[ts_idx(0, i, col)] = p[l];
+          else if (!inK)
+            T[ts_idx(0, col, i)] = p[l];
+        }
+        U[l * ldv + i] = ui[l];
+        V[l * ldv + i] = vi[l];
+      }
+    }
+    __syncthreads();
+    tsym_rank4(c, T, U, V, ldv, n);
+  }
+  const int tot = ts_extent(0, n);
+  _Pragma("unroll 1") for (int e = threadIdx.x; e < tot; e += NT) T[e] = -T[e];
+  __syncthreads();
+}
+#endif // PQP_BIG
+
 __device__ __forceinline__ int row_id(const Ctx& c, int s)
 {
   return s < c.ne ? s : c.ne + c.slot_cons[s];
@@ -833,7 +1208,28 @@ __device__ __forceinline__ int row_id(const Ctx& c, int s)
 // y = P^-1 v  (Pi = P^-1 explicit, full square n x ldn in the L2 workspace)
 __device__ __forceinline__ void apply_Pinv(const Ctx& c, const double* v, double* y)
 {
+#ifdef PQP_BIG
+  if (c.hess != PQP_HESSIAN_DENSE) { // P^-1 = diag(1 / (H_jj + rho)) (Diagonal) or I / rho (Zero)
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) y[j] = v[j] * c.d1inv[j];
+    __syncthreads();
+    return;
+  }
+#endif
   axpy_pass(c, c.Pi, c.ldn, c.n, v, c.n, y, nullptr, 1.0);
+}
+
+// out = Hmat x for the Hessian type of the batch (the tile kernel proper only takes dense Hessians)
+__device__ __forceinline__ void apply_H(const Ctx& c, const double* Hmat, const double* x, double* out)
+{
+#ifdef PQP_BIG
+  if (c.hess != PQP_HESSIAN_DENSE) {
+    const int n = c.n;
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) out[j] = (c.hess == PQP_HESSIAN_DIAGONAL) ? Hmat[(size_t)j * n + j] * x[j] : 0.0;
+    __syncthreads();
+    return;
+  }
+#endif
+  axpy_pass(c, Hmat, c.n, c.n, x, c.n, out, nullptr, 1.0);
 }
 
 // Solve K [ox; os] = [b1; b2],  K = [P B^T; B -Dlt], with the explicit block
@@ -975,6 +1371,22 @@ __device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_i
   PQP_VECS(c);
   const int ns = c.ns, cap = c.si_cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef PQP_BIG
+  (void)cap;
+  for (int s = warp; s < ns; s += NW) {
+    const int ids = row_id(c, s);
+    double* row = c.Si + ts_idx(0, s, 0);
+    for (int t = lane; t <= s; t += 32) {
+      const int idt = row_id(c, t);
+      row[t] = c.G[(size_t)max(ids, idt) * c.ldb + min(ids, idt)] + ((t == s) ? (s < c.ne ? mu_eq : mu_in) : 0.0);
+    }
+  }
+  __syncthreads();
+  tsym_sweep_invert(c, c.Si, v_scratch, c.uv_ld, ns);
+  if (threadIdx.x == 0) c.si_valid = 1;
+  __syncthreads();
+  return;
+#else
   const int nb = (ns + 31) >> 5;
   for (int bi = 0; bi < nb; ++bi) {
     const int rst = ts_rows(cap, bi);
@@ -996,6 +1408,7 @@ __device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_i
   tsym_sweep_invert(c, c.Si, v_scratch, c.uv_ld, ns);
   if (threadIdx.x == 0) c.si_valid = 1;
   __syncthreads();
+#endif
 }
 
 // P^-1 = (Hs + rho I)^-1, explicit: swept in the (free) S^-1 tile storage, then
@@ -1006,6 +1419,29 @@ __device__ __noinline__ void build_Pi(Ctx& c, double rho)
   PQP_VECS(c);
   const int n = c.n, cap = c.si_cap;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef PQP_BIG
+  (void)cap;
+  if (c.hess != PQP_HESSIAN_DENSE) {
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) c.d1inv[j] = 1.0 / (((c.hess == PQP_HESSIAN_DIAGONAL) ? c.Hs[(size_t)j * n + j] : 0.0) + rho);
+    __syncthreads();
+    return;
+  }
+  {
+    double* const work = c.Si; // packed region sized for max(n, capacity)
+    for (int i = warp; i < n; i += NW) {
+      double* row = work + ts_idx(0, i, 0);
+      const double* h = c.Hs + (size_t)i * n;
+      for (int j = lane; j <= i; j += 32) row[j] = h[j] + ((j == i) ? rho : 0.0);
+    }
+    __syncthreads();
+    tsym_sweep_invert(c, work, v_scratch, c.uv_ld, n);
+    for (int i = warp; i < n; i += NW) {
+      for (int j = lane; j < c.ldn; j += 32) c.Pi[(size_t)i * c.ldn + j] = (j < n) ? ts_get(work, 0, i, j) : 0.0;
+    }
+    __syncthreads();
+    return;
+  }
+#else
   const int nb = (n + 31) >> 5;
   double* const work = c.Si;
   for (int bi = 0; bi < nb; ++bi) {
@@ -1030,6 +1466,7 @@ __device__ __noinline__ void build_Pi(Ctx& c, double rho)
   __syncthreads();
   _Pragma("unroll 1") for (int e = threadIdx.x; e < tot; e += NT) work[e] = 0.0;
   __syncthreads();
+#endif
 }
 
 // Bt = [A_s; C_s]^T (n x ldb) in the L2 workspace
@@ -1060,6 +1497,16 @@ __device__ __noinline__ void build_Bt(Ctx& c)
 __device__ __noinline__ void build_G(Ctx& c)
 {
   const int n = c.n, m = c.m;
+#ifdef PQP_BIG
+  if (c.hess != PQP_HESSIAN_DENSE) { // W = P^-1 B^T with a diagonal P^-1: a row scaling of Bt
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < n; k += NW) {
+      const double d = c.d1inv[k];
+      for (int j = lane; j < c.ldb; j += 32) c.W[(size_t)k * c.ldb + j] = d * c.Bt[(size_t)k * c.ldb + j];
+    }
+    __syncthreads();
+  } else
+#endif
   gemm_tn(c.Pi, c.ldn, c.Bt, c.ldb, n, n, m, c.W, c.ldb, false); // W = Pi^T Bt (Pi symmetric)
   gemm_tn(c.Bt, c.ldb, c.W, c.ldb, n, m, m, c.G, c.ldb, true);   // G = Bt^T W, lower block triangle
 }
@@ -1097,7 +1544,7 @@ __device__ __noinline__ double kkt_residual(const Ctx& c, const Scal& sc, bool f
 {
   PQP_VECS(c);
   const int n = c.n, ne = c.ne, ns = c.ns;
-  axpy_pass(c, c.Hs, n, n, v_dx, n, v_hdx, nullptr, 1.0);                    // H dx (H symmetric)
+  apply_H(c, c.Hs, v_dx, v_hdx);                                             // H dx (H symmetric)
   axpy_pass(c, c.Bt, c.ldb, n, v_dx, c.m, v_adx, nullptr, 1.0);        // [A dx; C dx] (adx, cdx contiguous)
   // A^T dy + C_J^T dz_J is B^T lam of the solve that produced (dx, ds) (first call) or of the
   // refinement step just added to it: no third pass over the constraint rows
@@ -1147,7 +1594,15 @@ __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_setting
     PROF_ADD(PH_RESID, tp);
     ++it;
     double prev = err;
-    while (err >= eps) {
+#ifdef PQP_BIG
+    // Diagonal / zero Hessians (see pqp_solver_body.inl, iterative_solve): P^-1 reaches 1 / rho where H_jj = 0, the dual
+    // block is then badly conditioned and its explicit inverse less accurate than the reference's LDL^T; the refinement
+    // is driven down to 1e-10 instead of stopping at the inner tolerance so that the Newton steps stay as good.
+    const double eps_ref = (c.hess != PQP_HESSIAN_DENSE) ? fmin(eps, 1e-10) : eps;
+#else
+    const double eps_ref = eps;
+#endif
+    while (err >= eps_ref) {
       if (it >= S.nb_iterative_refinement) break;
       ++it;
       tp = PROF_T0();
@@ -1244,7 +1699,7 @@ __device__ __noinline__ void global_passes(Ctx& c, bool primal, bool dual)
   PQP_VECS(c);
   const int n = c.n, ne = c.ne, ni = c.ni;
   if (dual) {
-    axpy_pass(c, c.Hs, n, n, v_x, n, v_t1, nullptr, 1.0);
+    apply_H(c, c.Hs, v_x, v_t1);
     // A^T y and C^T z from one pass over Bt: coefficient vectors [y; 0] and [0; z]
     _Pragma("unroll 1") for (int id = threadIdx.x; id < c.ldb; id += NT) {
       c.kt[id] = (id < ne) ? v_y[id] : 0.0;
@@ -2096,7 +2551,7 @@ __device__ PQP_SOLVE_ONE_ATTR void solve_one(Ctx& c, const PqpSolveArgs& A, int 
   // objective 0.5 x^T H x + g^T x from the model (solver.hpp:1769-1781)
   double obj;
   {
-    axpy_pass(c, c.Hm, n, n, v_t1, n, v_t2, nullptr, 1.0);
+    apply_H(c, c.Hm, v_t1, v_t2);
     double part = 0;
     const double* gm = A.p.g + (size_t)q * n;
     _Pragma("unroll 1") for (int j = tid; j < n; j += NT) part += v_t1[j] * (0.5 * v_t2[j] + gm[j]);
@@ -2230,6 +2685,15 @@ __device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A)
     c.red = v + L.voff[V_RED];
     c.kt = v + L.voff[V_KT];
     c.kt2 = v + L.voff[V_KT2];
+#ifdef PQP_BIG
+    // big layout (kind 2): the pass scratch, the reduction scratch and the two coefficient vectors always live in shared
+    // memory (absolute offsets), whether or not the vector arena fits there
+    c.scratch = smem_dyn + L.voff[V_SCRATCH];
+    c.red = smem_dyn + L.voff[V_RED];
+    c.kt = smem_dyn + L.voff[V_KT];
+    c.kt2 = smem_dyn + L.voff[V_KT2];
+    c.vec_smem = L.in_smem[PA_VEC];
+#endif
     int* ib = reinterpret_cast<int*>(smem_dyn + L.smem_doubles);
     c.cons_slot = ib;
     c.slot_cons = c.cons_slot + A.d.nc;

@@ -63,6 +63,15 @@ namespace tilek {
 }
 #undef PQP_SM
 #define PQP_SM(p) ((void)0)
+// BIG variant of the tile body (layout kind 2): same driver, Gram precompute and AXPY-form passes, but loop-based
+// primitives on packed symmetric storage in the per-CTA global workspace: any n (even), any number of constraints,
+// dense / diagonal / zero Hessian, box constraints. Serves the shapes the tile kernel proper cannot hold in shared
+// memory (BASELINE cfg 3: dual block 200; cfg 4: n = 256; cfg 5: n = 500, diagonal Hessian, 1000 rows).
+#define PQP_BIG 1
+namespace bigk {
+#include "pqp_fast_body.inl"
+}
+#undef PQP_BIG
 #define PQP_WITH_BACKWARD 1
 namespace genk {
 #include "pqp_solver_body.inl"
@@ -691,8 +700,8 @@ pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream)
   const bool fast = a->lay.in_smem[PA_VEC] && a->lay.in_smem[PA_MS] && (a->lay.in_smem[PA_M1] || a->d.hess != PQP_HESSIAN_DENSE || symn <= symc);
   static const bool force_fused = std::getenv("PQP_FORCE_FUSED_KERNEL") != nullptr; // A/B hook: time the <1> instantiation on resident data
   const bool fused = a->ready != nullptr || a->fused_setup != 0 || force_fused;
-  auto kern = fused ? ((a->lay.kind == 1) ? tilek::pqp_solve_kernel_fused : (fast ? fastk::pqp_solve_kernel_fused : genk::pqp_solve_kernel_fused))
-                    : ((a->lay.kind == 1) ? tilek::pqp_solve_kernel : (fast ? fastk::pqp_solve_kernel : genk::pqp_solve_kernel));
+  auto kern = fused ? ((a->lay.kind == 1) ? tilek::pqp_solve_kernel_fused : (a->lay.kind == 2) ? bigk::pqp_solve_kernel_fused : (fast ? fastk::pqp_solve_kernel_fused : genk::pqp_solve_kernel_fused))
+                    : ((a->lay.kind == 1) ? tilek::pqp_solve_kernel : (a->lay.kind == 2) ? bigk::pqp_solve_kernel : (fast ? fastk::pqp_solve_kernel : genk::pqp_solve_kernel));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   PQP_LAUNCH(kern, grid, NT, smem, stream, *a);
