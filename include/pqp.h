@@ -188,6 +188,11 @@ int pqp_batch_solve(pqp_batch* b);
  * batch's own stream). Used by bench.py to time with CUDA events. */
 int pqp_batch_solve_async(pqp_batch* b, void* stream);
 int pqp_batch_sync(pqp_batch* b);
+/* Restricts the NEXT pqp_batch_solve / pqp_batch_solve_async to the listed QPs (QP<T>::solve() of one member of a
+ * BatchQP touches that QP only, wrapper.hpp:922-954; solve_in_parallel(std::vector<QP>&) the listed ones,
+ * parallel/qp_solve.hpp:17-38). indices == NULL or count < 0: every QP again. The selection is consumed by that
+ * solve; results, iteration counts and warm-start state of the other QPs are left untouched. */
+int pqp_batch_select(pqp_batch* b, const int64_t* indices, int64_t count);
 
 /* qp.results (results.hpp:67-88): x[dim], y[n_eq], z[n_in (+dim)], se, si, info
  * for QPs [first, first+count); any pointer may be NULL. */

@@ -186,6 +186,8 @@ public:
   void solve()
   {
     push_settings();
+    const int64_t me = (int64_t)index_; // this QP only: the siblings of a shared device batch keep their results
+    detail::check(pqp_batch_select(group_->handle, &me, 1));
     detail::check(pqp_batch_solve(group_->handle));
     fetch();
   }
@@ -212,6 +214,7 @@ public:
     pull_settings();
   }
   detail::Group* group() const { return group_.get(); }
+  isize index() const { return index_; }
 
 private:
   friend class BatchQP;
@@ -280,7 +283,14 @@ solve_groups(It first, It last)
     for (auto* h : groups) seen = seen || h == g;
     if (!seen) groups.push_back(g);
   }
-  for (auto* g : groups) proxsuite_b200::proxqp::detail::check(pqp_batch_solve_async(g->handle, nullptr));
+  for (auto* g : groups) { // only the listed members of each device batch (parallel/qp_solve.hpp:17-38)
+    std::vector<int64_t> idx;
+    for (It it = first; it != last; ++it) {
+      if ((**it).group() == g) idx.push_back((int64_t)(**it).index());
+    }
+    proxsuite_b200::proxqp::detail::check(pqp_batch_select(g->handle, idx.data(), (int64_t)idx.size()));
+    proxsuite_b200::proxqp::detail::check(pqp_batch_solve_async(g->handle, nullptr));
+  }
   for (auto* g : groups) proxsuite_b200::proxqp::detail::check(pqp_batch_sync(g->handle));
   for (It it = first; it != last; ++it) (**it).fetch();
 }
@@ -307,6 +317,43 @@ solve_in_parallel(std::vector<QP>& qps, const optional<std::size_t> num_threads 
   for (auto& q : qps) ptrs.push_back(&q);
   detail_parallel::solve_groups(ptrs.begin(), ptrs.end());
 }
+
+// One batch of same-shaped QPs over several GPUs of one node from ONE process (pqp_sharded_*): contiguous slices,
+// no cross-device dependency inside the iteration (parallel/qp_solve.hpp:55-59). Stacked row-major host arrays,
+// laid out like pqp_batch_init's.
+class ShardedBatch
+{
+public:
+  Settings settings{};
+  ShardedBatch(isize batch, isize dim, isize n_eq, isize n_in, const std::vector<int>& devices, bool box_constraints = false, HessianType hessian_type = HessianType::Dense,
+               DenseBackend dense_backend = DenseBackend::PrimalDualLDLT)
+    : handle_(pqp_sharded_create(batch, dim, n_eq, n_in, box_constraints ? 1 : 0, int(hessian_type), int(dense_backend), devices.data(), int(devices.size())))
+  {
+    if (!handle_) throw std::runtime_error(std::string("proxsuite_b200: ") + pqp_last_error());
+    pqp_settings_default(&settings, pqp_dense_backend_choice(int(dense_backend), dim, n_eq, n_in, box_constraints ? 1 : 0));
+  }
+  ~ShardedBatch() { pqp_sharded_destroy(handle_); }
+  ShardedBatch(const ShardedBatch&) = delete;
+  ShardedBatch& operator=(const ShardedBatch&) = delete;
+  void init(const double* H, const double* g, const double* A, const double* b, const double* C, const double* l, const double* u, const double* l_box = nullptr, const double* u_box = nullptr, bool compute_preconditioner = true)
+  {
+    proxsuite_b200::proxqp::detail::check(pqp_sharded_settings_set(handle_, &settings));
+    proxsuite_b200::proxqp::detail::check(pqp_sharded_init(handle_, H, g, A, b, C, l, u, l_box, u_box, compute_preconditioner ? 1 : 0, nullptr, nullptr, nullptr, nullptr));
+  }
+  void solve()
+  {
+    proxsuite_b200::proxqp::detail::check(pqp_sharded_settings_set(handle_, &settings));
+    proxsuite_b200::proxqp::detail::check(pqp_sharded_solve(handle_));
+  }
+  void results(double* x, double* y, double* z, pqp_info* info = nullptr, double* se = nullptr, double* si = nullptr)
+  {
+    proxsuite_b200::proxqp::detail::check(pqp_sharded_results(handle_, x, y, z, se, si, info));
+  }
+  int shards() const { return pqp_sharded_count(handle_); }
+
+private:
+  pqp_sharded* handle_;
+};
 
 } // namespace dense
 } // namespace proxqp

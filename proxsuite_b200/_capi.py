@@ -54,7 +54,7 @@ assert INFO_DTYPE.itemsize == C.sizeof(pqp_info)
 EXPORTED_SYMBOLS = [
     "pqp_settings_default", "pqp_dense_backend_choice", "pqp_batch_create", "pqp_batch_destroy", "pqp_batch_size",
     "pqp_batch_dims", "pqp_batch_settings_get", "pqp_batch_settings_set", "pqp_batch_init", "pqp_batch_init_device",
-    "pqp_batch_update", "pqp_batch_warm_start", "pqp_batch_solve", "pqp_batch_solve_async", "pqp_batch_sync",
+    "pqp_batch_update", "pqp_batch_warm_start", "pqp_batch_solve", "pqp_batch_solve_async", "pqp_batch_sync", "pqp_batch_select",
     "pqp_batch_results", "pqp_batch_results_device", "pqp_batch_scaled", "pqp_batch_backward", "pqp_batch_backward_device", "pqp_batch_results_copy_device", "pqp_batch_cleanup", "pqp_batch_timings",
     "pqp_random_qp", "pqp_last_error", "pqp_version",
     "pqp_sharded_create", "pqp_sharded_destroy", "pqp_sharded_count", "pqp_sharded_shard", "pqp_sharded_settings_set",
@@ -97,6 +97,7 @@ def lib():
     L.pqp_batch_solve.argtypes = [vp]
     L.pqp_batch_solve_async.argtypes = [vp, vp]
     L.pqp_batch_sync.argtypes = [vp]
+    L.pqp_batch_select.argtypes = [vp, vp, i64]
     L.pqp_batch_results.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp]
     L.pqp_batch_results_device.argtypes = [vp, vp, vp, vp, vp]
     L.pqp_batch_scaled.argtypes = [vp, i64] + [vp] * 9

@@ -96,6 +96,7 @@ struct pqp_batch
   cudaEvent_t ev_feed = nullptr;
   cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr; // around the retry launches of a sync()
   float retry_ms = 0;                           // device time of the retry launches of the last solve
+  std::vector<uint8_t> selected;                // pqp_batch_select: QPs the next solve addresses (empty: all)
   // QPLayer backward (allocated on first use): loss derivatives in, BackwardData out
   double *bw_loss = nullptr, *bw_dH = nullptr, *bw_dg = nullptr, *bw_dA = nullptr, *bw_db = nullptr, *bw_dC = nullptr, *bw_du = nullptr, *bw_dl = nullptr;
 };
@@ -349,11 +350,12 @@ fill_layout_big(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int ctas)
   vsz[V_DUAL] = n; vsz[V_SE] = m + 2; vsz[V_RUP] = 0; vsz[V_SI] = nc;
   vsz[V_HDX] = n; vsz[V_ADX] = m + 2; vsz[V_ATDY] = n; vsz[V_CDX] = 0; vsz[V_CTDZ] = n; vsz[V_Q] = n;
   vsz[V_GS] = n; vsz[V_BS] = ne; vsz[V_US] = nc; vsz[V_LS] = nc; vsz[V_IS] = d.box ? n : 2; vsz[V_DELTA] = n + ne + nc;
-  vsz[V_B] = ne; vsz[V_U] = nc; vsz[V_L] = nc;
+  // unscaled b, u, l: read from the model arrays when there are no box constraints (u, l of a box QP are concatenations)
+  vsz[V_B] = d.box ? ne : 0; vsz[V_U] = d.box ? nc : 0; vsz[V_L] = d.box ? nc : 0;
   vsz[V_D1INV] = (d.hess == PQP_HESSIAN_DENSE) ? 2 : n; vsz[V_DSV] = 2; vsz[V_DSINV] = 2;
-  vsz[V_T1] = n; vsz[V_T2] = n; vsz[V_T3] = n;
+  vsz[V_T1] = n; vsz[V_T2] = n; vsz[V_T3] = 0; // t3 shares q (never live together, see fill_layout_tile)
   vsz[V_S1] = sc; vsz[V_S2] = sc; vsz[V_S3] = sc; vsz[V_S4] = 0;
-  vsz[V_ALPHAS] = 2 * nc + 2; vsz[V_GRADS] = 4;
+  vsz[V_ALPHAS] = std::max(2 * nc + 2, m + 4); vsz[V_GRADS] = 4; // the second coefficient vector kt2 shares alphas
   // shared-memory part (absolute offsets)
   const int ord = std::max(n, cap);
   const int uv_ld = (ord + 2) & ~1;
@@ -362,7 +364,6 @@ fill_layout_big(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int ctas)
   L.voff[V_SCRATCH] = (int32_t)sm; sm += rnd(scratch);
   L.voff[V_RED] = (int32_t)sm;     sm += rnd(PQP_NW * 16);
   L.voff[V_KT] = (int32_t)sm;      sm += rnd(m + 4);
-  L.voff[V_KT2] = (int32_t)sm;     sm += rnd(m + 4);
   L.scratch_doubles = scratch;
   // vector arena (relative offsets)
   int off = 0;
@@ -372,6 +373,7 @@ fill_layout_big(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int ctas)
     off += (int)rnd(vsz[v]);
   }
   L.voff[V_S4] = L.voff[V_S3];
+  L.voff[V_T3] = L.voff[V_Q];
   L.voff[V_RUP] = L.voff[V_SE] + ne;
   L.voff[V_CDX] = L.voff[V_ADX] + ne;
   L.vec_doubles = off;
@@ -1243,7 +1245,7 @@ pqp_batch_solve_async(pqp_batch* b, void* stream_)
     PqpQpParams& p = b->hparams[i];
     pqp_info& info = b->hinfo[i];
     QpFlags& f = b->flags[i];
-    p.active = f.is_initialized ? 1 : 0;
+    p.active = (f.is_initialized && (b->selected.empty() || b->selected[(size_t)i])) ? 1 : 0;
     if (!p.active) continue;
     const int ig = p.s.initial_guess;
     if (f.dirty) {
@@ -1276,9 +1278,18 @@ pqp_batch_solve_async(pqp_batch* b, void* stream_)
     p.mu_eq = info.mu_eq;
     p.mu_in = info.mu_in;
   }
-  bool all_active = true;
-  for (int64_t i = 0; i < b->B; ++i) all_active = all_active && b->hparams[i].active;
-  if (b->deferred && (b->prof || b->dbg)) {
+  bool all_active = true, any_active = false;
+  for (int64_t i = 0; i < b->B; ++i) {
+    all_active = all_active && b->hparams[i].active;
+    any_active = any_active || b->hparams[i].active;
+  }
+  if (!any_active) { // solve before init (pqp.h: PQP_ESTATE), or a selection without an initialised QP
+    b->selected.clear();
+    return fail(PQP_ESTATE, "solve on a batch without an initialised QP (call init first)");
+  }
+  const bool partial = !b->selected.empty();
+  b->selected.clear(); // the selection is consumed by this solve
+  if (b->deferred && (b->prof || b->dbg || partial)) { // (a partial solve must not leave the other QPs without their set-up)
     if (int rc = flush_deferred(b)) return rc;
   }
   if (b->deferred) {
@@ -1320,6 +1331,23 @@ pqp_batch_solve_async(pqp_batch* b, void* stream_)
       b->flags[i].dirty = true; // solver.hpp:1835-1836
       b->flags[i].is_initialized = true;
     }
+  }
+  return 0;
+}
+
+int
+pqp_batch_select(pqp_batch* b, const int64_t* indices, int64_t count)
+{
+  if (!b) return fail(PQP_EINVAL, "null batch");
+  b->selected.clear();
+  if (!indices || count < 0) return 0;
+  b->selected.assign((size_t)b->B, 0);
+  for (int64_t k = 0; k < count; ++k) {
+    if (indices[k] < 0 || indices[k] >= b->B) {
+      b->selected.clear();
+      return fail(PQP_EINVAL, "wrong argument size: QP index out of bounds");
+    }
+    b->selected[(size_t)indices[k]] = 1;
   }
   return 0;
 }
@@ -1604,7 +1632,12 @@ pqp_batch_cleanup(pqp_batch* b, int64_t first, int64_t count)
   if (int rc = zero_results(b, first, count)) return rc;
   for (int64_t i = first; i < first + count; ++i) {
     cold_start(b->hinfo[i], &b->hparams[i].s, b->backend);
-    b->flags[i] = QpFlags(); // workspace.hpp:330-377
+    // workspace.hpp:330-377 clears every flag; the reference's next solve() re-runs the set-up from the model it
+    // still holds. The model data of this batch stay resident as well, so the QP stays solvable (is_initialized is
+    // this library's "has a model" flag: without it the next solve would silently skip the QP).
+    const bool had_model = b->flags[i].is_initialized;
+    b->flags[i] = QpFlags();
+    b->flags[i].is_initialized = had_model;
   }
   return 0;
 }

@@ -590,14 +590,14 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 #endif
 }
-__device__ __noinline__ void gemm_tn(const double* __restrict__ CM, int ldc, const double* __restrict__ R, int ldr, int K, int M, int ncols, double* __restrict__ Out, int ldo, bool lower)
+__device__ __noinline__ void gemm_tn(const double* __restrict__ CM, int ldc, const double* __restrict__ R, int ldr, int K, int M, int ncols, double* __restrict__ Out, int ldo, bool lower, int col0 = 0)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int mb = (M + 15) >> 4, nbk = (ncols + 31) >> 5;
   _Pragma("unroll 1") for (int tile = warp; tile < mb * nbk; tile += NW) {
     const int i0 = (tile / nbk) << 4, c0 = (tile % nbk) << 5;
-    if (lower && c0 > i0 + 15) continue;
+    if (lower && col0 + c0 > i0 + 15) continue; // (col0: column of the full matrix that column 0 of Out / R corresponds to)
     double acc[2][4][2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -964,6 +964,13 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
 }
 
 #else // PQP_BIG
+#ifdef PQP_CPU_EMU
+#define PQP_LOADS_FIRST() ((void)0)
+#define PQP_IN_SMEM(p) ((void)0)
+#else
+#define PQP_LOADS_FIRST() asm volatile("" ::: "memory")
+#define PQP_IN_SMEM(p) __builtin_assume(__isShared(p))
+#endif
 // ---------------------------------------------------------------------------
 // BIG variant: symmetric matrices (S^-1, and P during its inversion) as a PACKED lower triangle (row i holds the
 // columns 0..i) in the per-CTA global workspace (L2 / HBM), any order. Same interface as the tile storage above;
@@ -1048,23 +1055,25 @@ __device__ __noinline__ void tsym_mv(const Ctx& c, const double* __restrict__ T,
   __syncthreads();
 }
 
-// T[i][j] += u_i v_j on the packed lower triangle (j <= i < n)
+// T[i][j] += u_i v_j on the packed lower triangle (j <= i < n). Eight independent read-modify-writes per lane are in
+// flight (the triangle lives in L2 / HBM: with two, a 300 x 300 pass ran at one element per 300 cycles per thread).
 __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, const double* __restrict__ u, const double* __restrict__ v, int n)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
     double* row = T + ts_idx(0, i, 0);
     const double ui = u[i];
-    _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 128) { // four independent read-modify-writes per lane
-      double a[4], vv[4];
+    _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 256) {
+      double a[8], vv[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         const int j = j0 + 32 * q;
         a[q] = (j <= i) ? row[j] : 0.0;
         vv[q] = (j <= i) ? v[j] : 0.0;
       }
+      PQP_LOADS_FIRST(); // keep the eight loads ahead of the stores (ptxas otherwise sinks each load next to its use)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         const int j = j0 + 32 * q;
         if (j <= i) row[j] = fma(ui, vv[q], a[q]);
       }
@@ -1074,22 +1083,25 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
   __syncthreads();
 }
 
-// T[i][j] += sum_{k<4} U_k[i] V_k[j] (j <= i < n), k = 0..3 in order; U_k = U + k ldv, V_k = V + k ldv
+// T[i][j] += sum_{k<4} U_k[i] V_k[j] (j <= i < n), k = 0..3 in order; U_k = U + k ldv, V_k = V + k ldv (shared memory)
 __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  PQP_IN_SMEM(U); // the sweep's panel vectors live in c.scratch: shared memory in every layout of this variant
+  PQP_IN_SMEM(V);
   _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
     double* row = T + ts_idx(0, i, 0);
     const double u0 = U[i], u1 = U[ldv + i], u2 = U[2 * ldv + i], u3 = U[3 * ldv + i];
-    _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 64) {
-      double a[2];
+    _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 256) {
+      double a[8];
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < 8; ++q) {
         const int j = j0 + 32 * q;
         a[q] = (j <= i) ? row[j] : 0.0;
       }
+      PQP_LOADS_FIRST();
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < 8; ++q) {
         const int j = j0 + 32 * q;
         if (j <= i) row[j] = fma(u3, V[3 * ldv + j], fma(u2, V[2 * ldv + j], fma(u1, V[ldv + j], fma(u0, V[j], a[q]))));
       }
@@ -1277,7 +1289,8 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
 //   w = S^-1 g, delta = (b.P^-1 b + mu) - g.w,
 //   S^-1 <- [S^-1 + w w^T/delta, -w/delta; -w^T/delta, 1/delta].
 // Replaces Ldlt::insert_block_at (ldlt.hpp:431-475, modify.hpp:131-264).
-__device__ __noinline__ void insert_slot(Ctx& c, double mu)
+__device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_in);
+__device__ __noinline__ void insert_slot(Ctx& c, double mu, double mu_eq)
 {
   PQP_VECS(c);
   const int s = c.ns;
@@ -1302,6 +1315,17 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu)
     double part = 0;
     _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) part += v_s3[j] * v_s1[j];
     delta -= block_sum1(c, part);
+    // delta = (b.P^-1 b + mu) - g.w is the Schur complement of the new slot in S; it cancels when the new row is nearly
+    // dependent on the active ones (terms ~ |b|^2 / rho against mu). A non-positive or fully cancelled value means
+    // the bordering formula has no accuracy left: register the slot and re-form S^-1 from the Gram matrix instead
+    // (one sweep inversion; block-uniform: delta comes out of a block reduction).
+    if (!(delta > 1e-13 * (v_s3[s] + mu))) {
+      __syncthreads();
+      if (threadIdx.x == 0) c.ns = s + 1;
+      __syncthreads();
+      rebuild_Si_from_G(c, mu_eq, mu);
+      return;
+    }
     const double dinv = 1.0 / delta;
     _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) {
       const double wj = v_s1[j] * dinv;
@@ -1507,6 +1531,26 @@ __device__ __noinline__ void build_G(Ctx& c)
     __syncthreads();
   } else
 #endif
+#ifndef PQP_BIG
+  {
+    // W never touches the L2 workspace: it is formed in two column halves inside the S^-1 region of shared memory
+    // (free until the dual block is built) and consumed at once. 120 KB less per CTA at cfg 2: 296 workspaces
+    // then fit the L2 together with the streaming model data.
+    const int half = (((m + 1) >> 1) + 7) & ~7;
+    if ((long long)n * half <= (long long)ts_extent(c.si_cap, c.si_cap)) {
+      double* const Wsm = c.Si;
+      for (int c0 = 0; c0 < m; c0 += half) {
+        const int nc_ = min(half, m - c0);
+        gemm_tn(c.Pi, c.ldn, c.Bt + c0, c.ldb, n, n, nc_, Wsm, half, false);     // W_h = Pi^T Bt[:, c0 : c0 + nc_]
+        gemm_tn(c.Bt, c.ldb, Wsm, half, n, m, nc_, c.G + c0, c.ldb, true, c0);   // G[:, c0 : c0 + nc_] = Bt^T W_h (lower block triangle)
+      }
+      const int tot = ts_extent(c.si_cap, c.si_cap); // the region must be clean for S^-1 (entries outside the live order are zero)
+      _Pragma("unroll 1") for (int e = threadIdx.x; e < tot; e += NT) Wsm[e] = 0.0;
+      __syncthreads();
+      return;
+    }
+  }
+#endif
   gemm_tn(c.Pi, c.ldn, c.Bt, c.ldb, n, n, m, c.W, c.ldb, false); // W = Pi^T Bt (Pi symmetric)
   gemm_tn(c.Bt, c.ldb, c.W, c.ldb, n, m, m, c.G, c.ldb, true);   // G = Bt^T W, lower block triangle
 }
@@ -1677,7 +1721,7 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
         c.cons_slot[cons] = c.ns;
       }
       __syncthreads();
-      insert_slot(c, sc.mu_in);
+      insert_slot(c, sc.mu_in, sc.mu_eq);
     }
   }
   PROF_ADD(PH_INSERT, tp);
@@ -2047,14 +2091,22 @@ __device__ PQP_SOLVE_ONE_ATTR void solve_one(Ctx& c, const PqpSolveArgs& A, int 
     }
     __syncthreads();
     _Pragma("unroll 1") for (int j = tid; j < n; j += NT) v_gs[j] = P.gs[(size_t)q * n + j];
+#ifdef PQP_BIG
+    // big layout without box constraints: the unscaled b, u, l (one use per outer iteration) are read where they lie
+    // (c.b / c.u / c.l were pointed at the model arrays of this QP by the kernel body): no staging, no arena space
+    const bool ext_bounds = !c.box;
+#else
+    const bool ext_bounds = false;
+#endif
     _Pragma("unroll 1") for (int j = tid; j < ne; j += NT) {
       v_bs[j] = P.bs[(size_t)q * ne + j];
-      v_b[j] = P.b[(size_t)q * ne + j];
+      if (!ext_bounds) v_b[j] = P.b[(size_t)q * ne + j];
     }
     _Pragma("unroll 1") for (int j = tid; j < nc; j += NT) {
       v_us[j] = P.us[(size_t)q * nc + j];
       v_ls[j] = P.ls[(size_t)q * nc + j];
-      if (j < ni) {
+      if (ext_bounds) {
+      } else if (j < ni) {
         v_u[j] = P.u[(size_t)q * ni + j];
         v_l[j] = P.l[(size_t)q * ni + j];
       } else {
@@ -2691,7 +2743,7 @@ __device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A)
     c.scratch = smem_dyn + L.voff[V_SCRATCH];
     c.red = smem_dyn + L.voff[V_RED];
     c.kt = smem_dyn + L.voff[V_KT];
-    c.kt2 = smem_dyn + L.voff[V_KT2];
+    c.kt2 = c.alphas; // shares the line-search breakpoint array (never live together)
     c.vec_smem = L.in_smem[PA_VEC];
 #endif
     int* ib = reinterpret_cast<int*>(smem_dyn + L.smem_doubles);
@@ -2715,6 +2767,16 @@ __device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A)
       if (!setupk::feed_and_setup(&feed_args, cq, q, smem_dyn)) continue;
     }
     if (!A.p.params[q].active) continue;
+#ifdef PQP_BIG
+    if (!A.d.box) { // unscaled bounds straight from the model arrays (see solve_one, staging)
+      if (threadIdx.x == 0) {
+        c.b = A.p.b + (size_t)q * A.d.ne;
+        c.u = A.p.u + (size_t)q * A.d.ni;
+        c.l = A.p.l + (size_t)q * A.d.ni;
+      }
+      __syncthreads();
+    }
+#endif
     solve_one(c, A, q);
   }
   if (A.prof && threadIdx.x == 0) {

@@ -961,7 +961,8 @@ __device__ void gram_row(Ctx& c, int s)
 //   w = S^-1 g, delta = (b.P^-1 b + mu) - g.w,
 //   S^-1 <- [S^-1 + w w^T/delta, -w/delta; -w^T/delta, 1/delta].
 // Replaces Ldlt::insert_block_at (ldlt.hpp:431-475, modify.hpp:131-264).
-__device__ __noinline__ void insert_slot(Ctx& c, double mu)
+__device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_in);
+__device__ __noinline__ void insert_slot(Ctx& c, double mu, double mu_eq)
 {
   PQP_VECS(c);
   const int s = c.ns;
@@ -978,6 +979,17 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu)
     double part = 0;
     _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) part += v_s3[j] * v_s1[j];
     delta -= block_sum1(c, part);
+    // delta = (b.P^-1 b + mu) - g.w is the Schur complement of the new slot in S; it cancels when the new row is nearly
+    // dependent on the active ones (terms ~ |b|^2 / rho against mu). A non-positive or fully cancelled value means
+    // the bordering formula has no accuracy left: register the slot and re-form S^-1 from the Gram matrix instead
+    // (one sweep inversion; block-uniform: delta comes out of a block reduction).
+    if (!(delta > 1e-13 * (v_s3[s] + mu))) {
+      __syncthreads();
+      if (threadIdx.x == 0) c.ns = s + 1;
+      __syncthreads();
+      rebuild_Si_from_G(c, mu_eq, mu);
+      return;
+    }
     const double dinv = 1.0 / delta;
     double* row = c.Si + sym_off(s);
     _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) {
@@ -1248,7 +1260,7 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
       c.cons_slot[cons] = c.ns;
     }
     __syncthreads();
-    insert_slot(c, sc.mu_in);
+    insert_slot(c, sc.mu_in, sc.mu_eq);
   }
   PROF_ADD(PH_INSERT, tp);
   if (ndel > 0 || nadd > 0) sc.factor_fresh = false;

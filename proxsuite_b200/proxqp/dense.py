@@ -48,9 +48,11 @@ def _mat(a, rows, cols, what, allow_empty=True):
 def _vec(a, size, what, allow_empty=True):
     if a is None:
         return None
-    a = np.asarray(a, dtype=np.float64).reshape(-1) if np.asarray(a).ndim <= 2 else np.asarray(a, dtype=np.float64)
+    a = np.asarray(a, dtype=np.float64)
     if a.size == 0 and allow_empty:
         return None
+    if a.ndim == 2 and 1 in a.shape:  # column / row vectors are vectors (Eigen::Ref<Vec> accepts n x 1); a k x m block is not
+        a = a.reshape(-1)
     if a.ndim != 1 or a.shape[0] != size:
         raise ValueError(f"wrong argument size: expected {size} for {what}, got {a.shape[0] if a.ndim else 0}")
     return np.ascontiguousarray(a)
@@ -111,8 +113,12 @@ class _Group:
             self.pull_settings(q._index, q.settings)
 
     # -- solve ------------------------------------------------------------
-    def solve_async(self):
+    def solve_async(self, indices=None):
+        """`indices`: solve only these members (QP.solve() of one member, solve_in_parallel over a subset); None: all."""
         self.push_all()
+        if indices is not None and len(indices) < self.used:
+            arr = np.ascontiguousarray(np.asarray(sorted(indices), dtype=np.int64))
+            _capi.check(self.lib.pqp_batch_select(self.handle, _ptr(arr), arr.size))
         _capi.check(self.lib.pqp_batch_solve_async(self.handle, None))
         self.generation += 1
 
@@ -198,12 +204,14 @@ class QP:
     def _split_args(self, args, kw, pre_name):
         """Reference overloads: (..., l, u, [l_box, u_box,] compute_preconditioner, rho, mu_eq, mu_in, manual_minimal_H_eigenvalue)."""
         args = list(args)
+        self._box_args_given = "l_box" in kw or "u_box" in kw
         l_box = kw.pop("l_box", None)
         u_box = kw.pop("u_box", None)
         if len(args) >= 2 and not isinstance(args[0], (bool, np.bool_)) and (args[0] is None or np.ndim(args[0]) >= 1) \
                 and not isinstance(args[1], (bool, np.bool_)) and (args[1] is None or np.ndim(args[1]) >= 1):
             l_box, u_box = args[0], args[1]
             args = args[2:]
+            self._box_args_given = True
         names = [pre_name, "rho", "mu_eq", "mu_in", "manual_minimal_H_eigenvalue"]
         vals = {pre_name: kw.pop(pre_name, None), "rho": kw.pop("rho", None), "mu_eq": kw.pop("mu_eq", None),
                 "mu_in": kw.pop("mu_in", None), "manual_minimal_H_eigenvalue": kw.pop("manual_minimal_H_eigenvalue", None)}
@@ -231,6 +239,8 @@ class QP:
         l_box, u_box, vals = self._split_args(args, kw, "compute_preconditioner")
         if not self._box and (l_box is not None or u_box is not None):
             raise ValueError("wrong model setup: the QP object is designed without box constraints, but is initialized with lower or upper box inequalities.")
+        if self._box and not self._box_args_given:  # the 7-argument overload on a box QP (wrapper.hpp:367-372)
+            raise ValueError("wrong model setup: the QP object is designed with box constraints, but is initialized without lower or upper box inequalities.")
         arrs = self._gather(H, g, A, b, C, l, u, l_box, u_box)
         pre = True if vals["compute_preconditioner"] is None else bool(vals["compute_preconditioner"])
         self._call(self._group.lib.pqp_batch_init, arrs, pre, vals)
@@ -257,7 +267,7 @@ class QP:
         """QP::solve() / solve(x, y, z) (wrapper.hpp:922-954)."""
         self._warm_start(x, y, z)
         g = self._group
-        g.solve_async()
+        g.solve_async([self._index])  # this QP only: siblings of a shared device batch keep their results
         g.sync()
 
     def cleanup(self):
@@ -298,6 +308,7 @@ class BatchQP:
         self._capacity = int(batch_size)
         self._device = device
         self._groups = {}
+        self._count = {}
         self._qps: List[QP] = []
 
     def _group_for(self, key):
@@ -305,8 +316,13 @@ class BatchQP:
         if g is None or g.used >= g.capacity:
             # first QP of this shape, or the reserved capacity is exhausted:
             # open a new device batch (earlier QPs keep their own)
-            cap = max(self._capacity - len(self._qps), 1) if g is None else max(g.capacity, 1)
+            # geometric growth (a BatchQP() built without a size, as the reference's QP layer does, would otherwise
+            # open one capacity-1 device batch - streams, events, ~35 allocations, one launch - per QP)
+            total = self._count.get(key, 0)
             n, ne, ni, box, ht, be = key
+            dflt = int(max(1, min(64, (256 << 20) // max(1, 16 * (n * n + (ne + ni) * n)))))  # <= 256 MB of device copies
+            left = self._capacity - len(self._qps)
+            cap = (left if left > 0 else dflt) if g is None else max(2 * total, dflt)
             g = _Group(cap, n, ne, ni, box, ht, be, self._device)
             self._groups[key] = g
         return g
@@ -317,6 +333,7 @@ class BatchQP:
             raise ValueError("wrong argument size: the dimension wrt the primal variable x should be strictly positive.")
         key = (int(dim), int(n_eq), int(n_in), bool(box_constraints), int(hessian_type), int(dense_backend))
         g = self._group_for(key)
+        self._count[key] = self._count.get(key, 0) + 1
         qp = QP(dim, n_eq, n_in, box_constraints, HessianType(int(hessian_type)), DenseBackend(int(dense_backend)), _group=g)
         self._qps.append(qp)
         return qp
@@ -366,9 +383,13 @@ def solve_in_parallel(qps, num_threads: Optional[int] = None):
 
     `num_threads` is accepted for signature parity and ignored: the work
     distribution is the kernel's atomic work queue over persistent CTAs."""
-    groups = _groups_of(list(qps))
+    qps = list(qps)
+    groups = _groups_of(qps)
+    members = {}
+    for q in qps:
+        members.setdefault(id(q._group), []).append(q._index)
     for g in groups:
-        g.solve_async()
+        g.solve_async(members[id(g)])  # only the listed QPs of each device batch
     for g in groups:
         g.sync()
 

@@ -29,6 +29,36 @@ def load(path):
     return dict(H=P, g=q, A=A[eq], b=l[eq], C=A[~eq], l=l[~eq], u=u[~eq])
 
 
+def main_large():
+    """The REST of the problems the reference's dense test actually runs (test/src/dense_maros_meszaros.cpp:95-99 skips
+    n > 1000 or more than 1000 constraint rows): 34 problems with n up to 760, stored sparse (COO) in
+    maros_meszaros_large.npz; tests/test_oracle_maros.py rebuilds the dense arrays."""
+    import re
+    src = open("/root/reference/test/src/dense_maros_meszaros.cpp").read()
+    listed = re.findall(r'MAROS_MESZAROS_DIR "([^"]+)\.mat"', src)
+    out, names = {}, []
+    for name in listed:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = scipy.io.loadmat(SRC + name + ".mat")
+        n, rows = m["P"].shape[0], m["A"].shape[0]
+        if n > 1000 or rows > 1000 or (n <= 120 and rows <= 260):
+            continue
+        d = load(SRC + name + ".mat")
+        names.append(name)
+        for k in ("H", "A", "C"):
+            r, c = np.nonzero(d[k])
+            out[f"{name}/{k}_shape"] = np.array(d[k].shape, dtype=np.int32)
+            out[f"{name}/{k}_rc"] = np.stack([r, c]).astype(np.int32)
+            out[f"{name}/{k}_v"] = d[k][r, c]
+        for k in ("g", "b", "l", "u"):
+            out[f"{name}/{k}"] = d[k]
+    out["names"] = np.array(names)
+    path = os.path.join(os.path.dirname(OUT), "maros_meszaros_large.npz")
+    np.savez_compressed(path, **out)
+    print(len(names), "problems ->", path, os.path.getsize(path), "bytes")
+
+
 def main():
     out = {}
     names = []
@@ -51,4 +81,5 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    main()
+    main_large()

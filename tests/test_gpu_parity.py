@@ -254,6 +254,40 @@ def test_batch_equals_serial_bitwise(px, oracle):
     px.dense.solve_in_parallel(singles, 4)  # vector overload, num_threads accepted
 
 
+def test_solving_one_member_leaves_its_siblings_alone(px, oracle):
+    """QP<T>::solve() touches that QP only (wrapper.hpp:922-954) and solve_in_parallel(std::vector<QP>&) the listed
+    ones (parallel/qp_solve.hpp:17-38), although the members of a BatchQP share one device batch here
+    (pqp_batch_select): iteration counts and results of the other members must not change. A BatchQP() built without
+    a size (the reference's QP layer does that) must not open one device batch per QP."""
+    n, ne, ni = 12, 4, 6
+    data = [oracle.generate_qp("strongly_convex", i, n, ne, ni) for i in range(5)]
+    batch = px.dense.BatchQP()
+    for d in data:
+        qp = batch.init_qp_in_place(n, ne, ni)
+        qp.settings.eps_abs = EPS
+        qp.settings.eps_rel = 0
+        qp.init(*[d[k] for k in KEYS])
+    assert len({id(q._group) for q in batch}) == 1
+    px.dense.solve_in_parallel(batch)
+    first = [(q.results.info.iter, q.results.x.copy()) for q in batch]
+    assert all(it > 0 for it, _ in first)
+    batch[1].settings.initial_guess = px.InitialGuess.WARM_START_WITH_PREVIOUS_RESULT
+    batch[1].solve()
+    assert batch[1].results.info.iter == 0
+    for i in (0, 2, 3, 4):
+        assert batch[i].results.info.iter == first[i][0] and np.array_equal(batch[i].results.x, first[i][1])
+    batch[0].update(g=data[0]["g"] + 1.0)
+    batch[3].update(g=data[3]["g"] - 1.0)
+    px.dense.solve_in_parallel([batch[0], batch[3]])
+    assert not np.array_equal(batch[0].results.x, first[0][1]) and not np.array_equal(batch[3].results.x, first[3][1])
+    for i in (2, 4):
+        assert batch[i].results.info.iter == first[i][0] and np.array_equal(batch[i].results.x, first[i][1])
+    for i, dg in ((0, 1.0), (3, -1.0)):
+        d2 = dict(data[i], g=data[i]["g"] + dg)
+        pri, dua = kkt_residuals(d2, batch[i].results.x, batch[i].results.y, batch[i].results.z)
+        assert pri <= EPS and dua <= EPS
+
+
 def test_free_solve_function_and_errors(px, oracle):
     d = oracle.generate_qp("strongly_convex", 1, 12, 4, 6)
     r = px.dense.solve(d["H"], d["g"], d["A"], d["b"], d["C"], d["l"], d["u"], eps_abs=EPS, eps_rel=0)
@@ -479,6 +513,51 @@ def test_maros_meszaros_small_problems(px, oracle):
         qp.settings.initial_guess = px.InitialGuess.WARM_START_WITH_PREVIOUS_RESULT
         qp.solve()
         assert qp.results.info.iter == 0, name
+
+
+# problems of the larger set that are slow on the explicit-inverse path (thousands of Newton steps, tens of seconds on
+# one CTA) and the one it does not solve: run with PQP_TEST_SLOW=1 (tools/mm_gpu_debug.py prints all of them)
+MAROS_SLOW = ("QFORPLAN", "QSCAGR25")
+MAROS_UNSOLVED = ("QSCORPIO",)
+
+
+def test_maros_meszaros_rest_of_the_reference_list(px, oracle, monkeypatch):
+    """The other 34 problems the reference's dense Maros-Meszaros test runs (n up to 760, up to 856 constraint rows;
+    tests/golden/maros_meszaros_large.npz), through the C-ABI: status SOLVED, the reference's residual criteria,
+    the oracle's objective. Known gap, stated rather than hidden: QSCORPIO (degenerate LP-like problem, n = 358, 746
+    rows) is solved by the oracle's LDL^T in 68 Newton steps but NOT by the explicit-inverse GPU path (it keeps
+    re-forming the dual block and has not converged after minutes; the per-QP watchdog turns that into
+    MAX_ITER_REACHED); QFORPLAN / QSCAGR25 are solved but need 1.5x / 19x the oracle's Newton steps."""
+    from test_oracle_maros import EPS as MEPS, check_reference_criteria, problems_large
+
+    slow = os.environ.get("PQP_TEST_SLOW") == "1"
+    monkeypatch.setenv("PQP_WATCHDOG_MS", "120000" if slow else "30000")
+    done = 0
+    for name, d in problems_large():
+        if not slow and (name in MAROS_SLOW or name in MAROS_UNSOLVED):
+            continue
+        n, ne, ni = d["H"].shape[0], d["A"].shape[0], d["C"].shape[0]
+        qo = oracle.OracleQP(n, ne, ni, dense_backend=oracle.BACKEND_AUTOMATIC)
+        qo.set(eps_abs=MEPS, eps_rel=0.0, eps_primal_inf=1e-12, eps_dual_inf=1e-12)
+        qo.init(**d)
+        ro = qo.solve()
+        qp = px.dense.QP(n, ne, ni, False, px.HessianType.Dense, px.DenseBackend.Automatic)
+        qp.settings.eps_abs = MEPS
+        qp.settings.eps_rel = 0
+        qp.settings.eps_primal_inf = 1e-12
+        qp.settings.eps_dual_inf = 1e-12
+        qp.init(d["H"], d["g"], d["A"], d["b"], d["C"], d["l"], d["u"])
+        qp.solve()
+        r = qp.results
+        if name in MAROS_UNSOLVED:
+            assert ro.info.status == 0 and int(r.info.status) != 0, name  # the day this fails the gap is closed
+            continue
+        assert int(r.info.status) == ro.info.status == 0, (name, int(r.info.status), r.info.iter)
+        check_reference_criteria(d, r.x, r.y, r.z)
+        obj_o = 0.5 * ro.x @ d["H"] @ ro.x + d["g"] @ ro.x
+        assert abs(r.info.objValue - obj_o) <= 1e-5 * max(1.0, abs(obj_o)), name
+        done += 1
+    assert done == (33 if slow else 31)
 
 
 @pytest.mark.gpu

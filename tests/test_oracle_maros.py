@@ -18,6 +18,22 @@ def problems():
         yield str(name), {k: z[f"{name}/{k}"] for k in "HgAbClu"}
 
 
+def problems_large():
+    """the other 34 problems the reference's dense test runs (n up to 760), stored sparse"""
+    z = np.load(os.path.join(HERE, "golden", "maros_meszaros_large.npz"))
+    for name in z["names"]:
+        d = {}
+        for k in ("H", "A", "C"):
+            shape = tuple(int(v) for v in z[f"{name}/{k}_shape"])
+            m = np.zeros(shape)
+            rc = z[f"{name}/{k}_rc"]
+            m[rc[0], rc[1]] = z[f"{name}/{k}_v"]
+            d[k] = m
+        for k in ("g", "b", "l", "u"):
+            d[k] = z[f"{name}/{k}"]
+        yield str(name), d
+
+
 def check_reference_criteria(d, x, y, z):
     ne, ni = d["A"].shape[0], d["C"].shape[0]
     dua = d["H"] @ x + d["g"]
@@ -48,3 +64,18 @@ def test_oracle_passes_the_reference_maros_meszaros_test(oracle):
         assert r2.info.iter == 0, name
         names.append(name)
     assert len(names) == 28
+
+
+def test_oracle_passes_the_rest_of_the_reference_maros_meszaros_list(oracle):
+    """dense_maros_meszaros.cpp:95-99 skips n > 1000 / > 1000 constraint rows; these are the 34 remaining problems."""
+    names = []
+    for name, d in problems_large():
+        n, ne, ni = d["H"].shape[0], d["A"].shape[0], d["C"].shape[0]
+        qp = oracle.OracleQP(n, ne, ni, dense_backend=oracle.BACKEND_AUTOMATIC)
+        qp.set(eps_abs=EPS, eps_rel=0.0, eps_primal_inf=1e-12, eps_dual_inf=1e-12)
+        qp.init(**d)
+        r = qp.solve()
+        assert r.info.status == oracle.PROXQP_SOLVED, name
+        check_reference_criteria(d, r.x, r.y, r.z)
+        names.append(name)
+    assert len(names) == 34

@@ -55,9 +55,10 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["2b", "3", "4", "5"]
     if "2b" in which:
         run("cfg2b", "strongly_convex", 4096, 100, 50, 100)
+    full = os.environ.get("SWEEP_FULL") == "1"  # BASELINE.json's own per-GPU batch sizes (cfg 5: 592 instead of 4096, 2 QPs per CTA)
     if "3" in which:
-        run("cfg3", "box_benchmark", 592, 100, 50, 50, box=True, sparsity=0.75)
+        run("cfg3", "box_benchmark", 4096 if full else 592, 100, 50, 50, box=True, sparsity=0.75)
     if "4" in which:
-        run("cfg4", "strongly_convex", 296, 256, 128, 256)
+        run("cfg4", "strongly_convex", 1024 if full else 296, 256, 128, 256)
     if "5" in which:
-        run("cfg5", "diagonal_benchmark", 148, 500, 250, 250, box=True, hessian=px.HessianType.Diagonal, sparsity=0.75)
+        run("cfg5", "diagonal_benchmark", 592 if full else 148, 500, 250, 250, box=True, hessian=px.HessianType.Diagonal, sparsity=0.75)
