@@ -97,6 +97,7 @@ struct pqp_batch
   cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr; // around the retry launches of a sync()
   float retry_ms = 0;                           // device time of the retry launches of the last solve
   std::vector<uint8_t> selected;                // pqp_batch_select: QPs the next solve addresses (empty: all)
+  int64_t l2_window_bytes = 0, l2_persist_bytes = 0; // access-policy window of the workspace (0: unsupported)
   // QPLayer backward (allocated on first use): loss derivatives in, BackwardData out
   double *bw_loss = nullptr, *bw_dH = nullptr, *bw_dg = nullptr, *bw_dA = nullptr, *bw_db = nullptr, *bw_dC = nullptr, *bw_du = nullptr, *bw_dl = nullptr;
 };
@@ -840,6 +841,25 @@ enqueue_solve(pqp_batch* b, cudaStream_t st, const PqpLayout& lay, int grid, int
     if (b->d.ni > 0) mn = std::min<int64_t>(mn, b->d.ni);
     a.feed_margin = (int32_t)((128 + 8 * mn - 1) / (8 * mn));
   }
+#ifndef PQP_CPU_EMU
+  // L2 residency experiment (PQP_L2_PERSIST=1; OFF by default): an access-policy window that marks the per-CTA workspace
+  // (P^-1, Bt, G: ~300 KB x 296 CTAs at cfg 2) as persisting in L2 and everything else as streaming. Measured (round 2,
+  // profiles/r02_summary.md section 6): no effect on the tile kernel (31.4 vs 31.5 ms, DRAM traffic 9.1 GB either way)
+  // and 20 % SLOWER on the large shapes, whose multi-GB workspaces the window cannot cover.
+  {
+    static const bool persist = std::getenv("PQP_L2_PERSIST") && std::atoi(std::getenv("PQP_L2_PERSIST")) == 1;
+    if (persist && b->ws && b->l2_window_bytes > 0) {
+      cudaStreamAttrValue at{};
+      at.accessPolicyWindow.base_ptr = (void*)a.ws;
+      at.accessPolicyWindow.num_bytes = (size_t)std::min<int64_t>(b->l2_window_bytes, (int64_t)grid * lay.ws_doubles * 8);
+      at.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)b->l2_persist_bytes / (double)std::max<size_t>(at.accessPolicyWindow.num_bytes, 1));
+      at.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      at.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &at); // best effort: an error here must not fail the solve
+      (void)cudaGetLastError();
+    }
+  }
+#endif
   if (timed) CUDA_TRY(cudaEventRecord(b->ev2, st));
   int rc = pqp_launch_solve(&a, grid, st);
   if (rc != 0) return fail(PQP_ECUDA, std::string("solve kernel launch: ") + cudaGetErrorString((cudaError_t)rc));
@@ -1069,6 +1089,21 @@ pqp_batch_create(int64_t batch, int64_t dim, int64_t n_eq, int64_t n_in, int box
       pqp_batch_destroy(b);
       return nullptr;
     }
+#ifndef PQP_CPU_EMU
+    {
+      int max_persist = 0, max_window = 0;
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+      cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+      if (max_persist > 0 && max_window > 0) {
+        const size_t want = std::min<size_t>((size_t)max_persist, ws * sizeof(double));
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+          b->l2_persist_bytes = (int64_t)want;
+          b->l2_window_bytes = (int64_t)std::min<size_t>((size_t)max_window, ws * sizeof(double));
+        }
+        (void)cudaGetLastError();
+      }
+    }
+#endif
   }
   if (std::getenv("PQP_PROFILE")) dev_alloc(b, &b->prof, 16);
   if (std::getenv("PQP_DEBUG_TRACE")) {
