@@ -502,8 +502,10 @@ __device__ __noinline__ void bt_dot_big(const Ctx& c, const double* __restrict__
 {
   constexpr int NCH = 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = c.n, np = c.ldb >> 1;
+  // box constraints: only the [A_s; C_s] columns of Bt are streamed, the box block (i_s[j] e_j) enters as one term per row
+  const int n = c.n, nr = c.ne + c.ni, np = c.box ? ((nr + 1) >> 1) : (c.ldb >> 1);
   const bool two = coef2 != nullptr;
+  const bool odd_tail = c.box && (nr & 1); // the last streamed pair then holds the first box column: masked
   _Pragma("unroll 1") for (int jb = warp; jb < n; jb += 4 * NW) {
     double d1[4] = { 0.0, 0.0, 0.0, 0.0 }, d2[4] = { 0.0, 0.0, 0.0, 0.0 };
     _Pragma("unroll 1") for (int g0 = 0; g0 < np; g0 += 32 * NCH) {
@@ -521,7 +523,10 @@ __device__ __noinline__ void bt_dot_big(const Ctx& c, const double* __restrict__
         const int j = jb + u * NW;
         const double2* rp = reinterpret_cast<const double2*>(c.Bt + (size_t)(j < n ? j : 0) * c.ldb) + g0 + lane;
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch) v[u][ch] = (j < n && pv[ch]) ? rp[32 * ch] : make_double2(0.0, 0.0);
+        for (int ch = 0; ch < NCH; ++ch) {
+          v[u][ch] = (j < n && pv[ch]) ? rp[32 * ch] : make_double2(0.0, 0.0);
+          if (odd_tail && g0 + lane + 32 * ch == np - 1) v[u][ch].y = 0.0;
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -541,9 +546,14 @@ __device__ __noinline__ void bt_dot_big(const Ctx& c, const double* __restrict__
     if ((lane & 7) == 0) {
       const int j = jb + (lane >> 3) * NW;
       if (j < n) {
-        out1[j] = (add ? add[j] : 0.0) + sign * d1[0];
-        if (raw1) raw1[j] = d1[0];
-        if (two) out2[j] = d2[0];
+        double r1 = d1[0], r2 = d2[0];
+        if (c.box) {
+          r1 = fma(c.is[j], coef1[nr + j], r1);
+          if (two) r2 = fma(c.is[j], coef2[nr + j], r2);
+        }
+        out1[j] = (add ? add[j] : 0.0) + sign * r1;
+        if (raw1) raw1[j] = r1;
+        if (two) out2[j] = r2;
       }
     }
   }
@@ -1244,6 +1254,23 @@ __device__ __forceinline__ void apply_H(const Ctx& c, const double* Hmat, const 
   axpy_pass(c, Hmat, c.n, c.n, x, c.n, out, nullptr, 1.0);
 }
 
+// out[0 .. m) = [A_s; C_s; box rows] coef = Bt^T coef (AXPY form over the rows of Bt)
+__device__ __forceinline__ void bt_axpy(const Ctx& c, const double* coef, double* out)
+{
+#ifdef PQP_BIG
+  if (c.box) {
+    // the box block of Bt is the scaled identity pattern i_s[k] e_k: its n x n zeros are not streamed (half of every
+    // constraint pass at cfg 3 / cfg 5); the products are exact copies of what the dense pass would give
+    const int nr = c.ne + c.ni;
+    axpy_pass(c, c.Bt, c.ldb, c.n, coef, nr, out, nullptr, 1.0);
+    _Pragma("unroll 1") for (int k = threadIdx.x; k < c.n; k += NT) out[nr + k] = coef[k] * c.is[k];
+    __syncthreads();
+    return;
+  }
+#endif
+  axpy_pass(c, c.Bt, c.ldb, c.n, coef, c.m, out, nullptr, 1.0);
+}
+
 // Solve K [ox; os] = [b1; b2],  K = [P B^T; B -Dlt], with the explicit block
 // inverses:  t = P^-1 b1;  lam = S^-1 (B t - b2);  x = P^-1 (b1 - B^T lam).
 // In place allowed (ox == b1, os == b2). Replaces Ldlt::solve_in_place
@@ -1263,7 +1290,7 @@ __device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const dou
   }
   apply_Pinv(c, b1, v_t1);
   // B t for every row of [A_s; C_s] at once (Bt = B^T), then pick the slots
-  axpy_pass(c, c.Bt, c.ldb, n, v_t1, c.m, c.kt, nullptr, 1.0);
+  bt_axpy(c, v_t1, c.kt);
   _Pragma("unroll 1") for (int s = threadIdx.x; s < ns; s += NT) v_s1[s] = c.kt[row_id(c, s)] - b2[s];
   __syncthreads();
   tsym_mv(c, c.Si, v_s1, os, ns);
@@ -1346,23 +1373,137 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu, double mu_eq)
 //   S'^-1 = T - q q^T / T_kk   (T = S^-1 without row/column k, q = column k),
 // then the last slot takes the place of k (slot order carries no meaning).
 // Replaces Ldlt::delete_at (ldlt.hpp:340-387).
-__device__ __noinline__ void delete_slot(Ctx& c, int k)
+// Append kcnt (2..4) dual slots at once: slots s0 .. s0 + kcnt - 1 (s0 == c.ns) are already registered. Block
+// bordering of the explicit inverse with Gn = Gram columns of the new rows against the old slots, D = their own Gram
+// block + mu I:   W = S^-1 Gn,   Dl = D - Gn^T W,
+//   S^-1 <- [ S^-1 + W Dl^-1 W^T,  -W Dl^-1 ;  -Dl^-1 W^T,  Dl^-1 ]
+// kcnt read-only mat-vecs and ONE rank-4 pass over S^-1 instead of kcnt mat-vecs and kcnt rank-1 passes (a
+// read-modify-write pass costs twice a mat-vec on the stored triangle). The k x k Schur block is inverted
+// redundantly by every thread; a pivot that has cancelled sends the whole group to the re-formation from G.
+__device__ __noinline__ void insert_block(Ctx& c, int kcnt, double mu, double mu_eq)
+{
+  PQP_VECS(c);
+  const int s0 = c.ns, cap = c.si_cap, ldv = c.uv_ld;
+  if (s0 + kcnt > cap) { // does not fit the shared-memory S^-1: hand the QP to the generic kernel
+    if (threadIdx.x == 0) c.overflow = 1;
+    __syncthreads();
+    return;
+  }
+  double* T = c.Si;
+  // W columns are parked in slot-sized vectors that are free during an active-set change (rhs / err / step of the solve)
+  double* const Wst[4] = { v_rs, v_es, v_ds, v_s2 };
+  double dl[4][4]; // D - Gn^T W, identity padded
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dl[p][q] = (p == q) ? 1.0 : 0.0;
+  }
+  double dscale[4] = { 1.0, 1.0, 1.0, 1.0 };
+  for (int a = 0; a < kcnt; ++a) {
+    const int ids = row_id(c, s0 + a);
+    _Pragma("unroll 1") for (int j = threadIdx.x; j <= s0 + a; j += NT) {
+      const int idj = row_id(c, j);
+      v_s3[j] = c.G[(size_t)max(ids, idj) * c.ldb + min(ids, idj)];
+    }
+    __syncthreads();
+    double part[4] = { 0.0, 0.0, 0.0, 0.0 };
+    double dummy[1] = { 0.0 };
+    if (s0 > 0) {
+      tsym_mv(c, T, v_s3, v_s1, s0);
+      _Pragma("unroll 1") for (int j = threadIdx.x; j < s0; j += NT) {
+        const double wj = v_s1[j];
+        Wst[a][j] = wj;
+      }
+      __syncthreads();
+      _Pragma("unroll 1") for (int j = threadIdx.x; j < s0; j += NT) {
+        const double gj = v_s3[j];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b <= a) part[b] = fma(gj, Wst[b][j], part[b]);
+        }
+      }
+      block_reduce<4, 0>(c, part, dummy);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (b <= a) {
+        const double dab = v_s3[s0 + b] + ((b == a) ? mu : 0.0);
+        const double v = dab - part[b];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if ((p == a && q == b) || (p == b && q == a)) dl[p][q] = v;
+          }
+        }
+        if (b == a) dscale[a] = dab;
+      }
+    }
+    __syncthreads();
+  }
+  // Dl^-1 by Gauss-Jordan (SPD); a cancelled pivot means the bordering has no accuracy left
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    bad = bad || !(dl[k][k] > 1e-13 * dscale[k]);
+    const double inv = 1.0 / dl[k][k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dl[k][q] = (q == k) ? inv : dl[k][q] * inv;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (p != k) {
+        const double f = dl[p][k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dl[p][q] = (q == k) ? -f * inv : fma(-f, dl[k][q], dl[p][q]);
+      }
+    }
+  }
+  if (bad) { // block-uniform: dl comes out of block reductions
+    if (threadIdx.x == 0) c.ns = s0 + kcnt;
+    __syncthreads();
+    rebuild_Si_from_G(c, mu_eq, mu);
+    return;
+  }
+  double* const U = v_scratch;
+  double* const V = v_scratch + 4 * ldv;
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < s0; i += NT) {
+    double w[4], u[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) w[a] = (a < kcnt) ? Wst[a][i] : 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) u[a] = (a < kcnt) ? (w[0] * dl[0][a] + w[1] * dl[1][a] + w[2] * dl[2][a] + w[3] * dl[3][a]) : 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      V[a * ldv + i] = w[a];
+      if (a < kcnt) ts_put(T, cap, s0 + a, i, -u[a]);
+    }
+#ifdef PQP_BIG
+#pragma unroll
+    for (int a = 0; a < 4; ++a) U[a * ldv + i] = u[a];
+#else
+    reinterpret_cast<double2*>(U)[2 * i] = make_double2(u[0], u[1]);
+    reinterpret_cast<double2*>(U)[2 * i + 1] = make_double2(u[2], u[3]);
+#endif
+  }
+  if (threadIdx.x == 0) {
+    for (int a = 0; a < kcnt; ++a) {
+      for (int b = 0; b <= a; ++b) ts_put(T, cap, s0 + a, s0 + b, dl[a][b]);
+    }
+  }
+  __syncthreads();
+  if (s0 > 0) tsym_rank4(c, T, U, V, ldv, s0);
+  if (threadIdx.x == 0) c.ns = s0 + kcnt;
+  __syncthreads();
+}
+
+// Storage part of a deletion: the last slot takes the place of slot k (slot order carries no meaning), the freed last
+// row / column is cleared, the slot maps are updated. Rows / columns of k must already be decoupled from the rest.
+__device__ __noinline__ void drop_slot(Ctx& c, int k)
 {
   PQP_VECS(c);
   const int ns = c.ns, cap = c.si_cap, L = ns - 1;
   double* T = c.Si;
-  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = ts_get(T, cap, i, k);
   __syncthreads();
-  const double sinv = -1.0 / v_s1[k];
-  __syncthreads();
-  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
-    const double q = (i == k) ? 0.0 : v_s1[i]; // row / column k are dropped below
-    v_s2[i] = q;
-    v_s3[i] = q * sinv;
-  }
-  __syncthreads();
-  tsym_rank1(c, T, v_s2, v_s3, ns);
-  // move row / column L into k, clear row / column L
   _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = ts_get(T, cap, i, L);
   __syncthreads();
   _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
@@ -1384,6 +1525,108 @@ __device__ __noinline__ void delete_slot(Ctx& c, int k)
     c.ns = L;
   }
   __syncthreads();
+}
+
+__device__ __noinline__ void delete_slot(Ctx& c, int k)
+{
+  PQP_VECS(c);
+  const int ns = c.ns, cap = c.si_cap, L = ns - 1;
+  double* T = c.Si;
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = ts_get(T, cap, i, k);
+  __syncthreads();
+  const double sinv = -1.0 / v_s1[k];
+  __syncthreads();
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
+    const double q = (i == k) ? 0.0 : v_s1[i]; // row / column k are dropped below
+    v_s2[i] = q;
+    v_s3[i] = q * sinv;
+  }
+  __syncthreads();
+  tsym_rank1(c, T, v_s2, v_s3, ns);
+  drop_slot(c, k);
+}
+
+// Remove up to four dual slots at once (ks[0 .. kcnt), all >= ne, distinct): block form of the Schur complement,
+//   S'^-1 = T_RR - Q (T_KK)^-1 Q^T,   Q = T[:, K],
+// as ONE rank-4 pass over S^-1 instead of kcnt rank-1 passes (deletions come in groups: most of the cost of a
+// deletion is streaming the stored triangle). The k x k block is inverted redundantly by every thread (it is a
+// principal block of an SPD matrix: Gauss-Jordan without pivoting), rows / columns K stay untouched (zero rows of U,
+// zero columns of V) and are dropped afterwards, last slot into freed position, highest position first.
+__device__ __noinline__ void delete_block(Ctx& c, int kcnt, int k0, int k1, int k2, int k3)
+{
+  PQP_VECS(c);
+  const int ns = c.ns, cap = c.si_cap, ldv = c.uv_ld;
+  double* T = c.Si;
+  double* const U = v_scratch;
+  double* const V = v_scratch + 4 * ldv;
+  const int ks[4] = { k0, k1, k2, k3 };
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) V[a * ldv + i] = (a < kcnt) ? ts_get(T, cap, i, ks[a]) : 0.0;
+  }
+  __syncthreads();
+  double w[4][4]; // becomes -(T_KK)^-1, identity padded
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[p][q] = (p < kcnt && q < kcnt) ? V[q * ldv + ks[p]] : ((p == q) ? 1.0 : 0.0);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { // in-place Gauss-Jordan inverse
+    const double inv = 1.0 / w[k][k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[k][q] = (q == k) ? inv : w[k][q] * inv;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (p != k) {
+        const double f = w[p][k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[p][q] = (q == k) ? -f * inv : fma(-f, w[k][q], w[p][q]);
+      }
+    }
+  }
+  __syncthreads(); // every thread has read the block before rows K of V are cleared
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
+    bool inK = false;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) inK = inK || (a < kcnt && i == ks[a]);
+    double q[4], u[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) q[a] = V[a * ldv + i];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) u[a] = inK ? 0.0 : -(q[0] * w[0][a] + q[1] * w[1][a] + q[2] * w[2][a] + q[3] * w[3][a]);
+    if (inK) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) V[a * ldv + i] = 0.0;
+    }
+#ifdef PQP_BIG
+#pragma unroll
+    for (int a = 0; a < 4; ++a) U[a * ldv + i] = u[a];
+#else
+    reinterpret_cast<double2*>(U)[2 * i] = make_double2(u[0], u[1]);
+    reinterpret_cast<double2*>(U)[2 * i + 1] = make_double2(u[2], u[3]);
+#endif
+  }
+  __syncthreads();
+  tsym_rank4(c, T, U, V, ldv, ns);
+  // drop the slots, highest position first (a lower position is never the "last slot" of a later drop)
+  int order[4] = { k0, k1, k2, k3 };
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (a >= kcnt) order[a] = -1;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int b = 0; b < 3 - a; ++b) {
+      if (order[b] < order[b + 1]) {
+        const int t = order[b];
+        order[b] = order[b + 1];
+        order[b + 1] = t;
+      }
+    }
+  }
+  for (int a = 0; a < kcnt; ++a) drop_slot(c, order[a]);
 }
 
 // S^-1 from the cached Gram matrix with the given proximal parameters
@@ -1589,7 +1832,7 @@ __device__ __noinline__ double kkt_residual(const Ctx& c, const Scal& sc, bool f
   PQP_VECS(c);
   const int n = c.n, ne = c.ne, ns = c.ns;
   apply_H(c, c.Hs, v_dx, v_hdx);                                             // H dx (H symmetric)
-  axpy_pass(c, c.Bt, c.ldb, n, v_dx, c.m, v_adx, nullptr, 1.0);        // [A dx; C dx] (adx, cdx contiguous)
+  bt_axpy(c, v_dx, v_adx);                                                 // [A dx; C dx] (adx, cdx contiguous)
   // A^T dy + C_J^T dz_J is B^T lam of the solve that produced (dx, ds) (first call) or of the
   // refinement step just added to it: no third pass over the constraint rows
   double m = 0;
@@ -1686,7 +1929,19 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
     return !(c.act_up[cons] || c.act_low[cons]);
   });
   long long tp = PROF_T0();
-  for (int k = ndel - 1; k >= 0; --k) delete_slot(c, c.ne + c.list1[k]);
+  for (int k = ndel - 1; k >= 0;) { // from the last slot to the first, four at a time
+#ifdef PQP_BIG
+    const int cnt = min(4, k + 1);
+#else
+    const int cnt = 1; // shared-memory S^-1 (tile kernel): a pass is cheap, the block form only adds code (measured: -6 % at cfg 2)
+#endif
+    if (cnt == 1) {
+      delete_slot(c, c.ne + c.list1[k]);
+    } else {
+      delete_block(c, cnt, c.ne + c.list1[k], c.ne + c.list1[k - 1], cnt > 2 ? c.ne + c.list1[k - 2] : -1, cnt > 3 ? c.ne + c.list1[k - 3] : -1);
+    }
+    k -= cnt;
+  }
   PROF_ADD(PH_DELETE, tp);
   tp = PROF_T0();
   int nadd = block_compact(c, c.nc, c.list1, [&](int i) { return (c.act_up[i] || c.act_low[i]) && c.cons_slot[i] < 0; });
@@ -1714,14 +1969,26 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
       rebuild_Si_from_G(c, sc.mu_eq, sc.mu_in);
     }
   } else {
-    for (int k = 0; k < nadd; ++k) {
-      if (threadIdx.x == 0) {
-        int cons = c.list1[k];
-        c.slot_cons[c.ns] = cons;
-        c.cons_slot[cons] = c.ns;
+    for (int k = 0; k < nadd;) { // four at a time where S^-1 is streamed from L2 / HBM (big variant)
+#ifdef PQP_BIG
+      const int cnt = min(4, nadd - k);
+#else
+      const int cnt = 1;
+#endif
+      const int s0 = c.ns;
+      __syncthreads();
+      if (threadIdx.x < cnt) {
+        const int cons = c.list1[k + threadIdx.x];
+        c.slot_cons[s0 + threadIdx.x] = cons;
+        c.cons_slot[cons] = s0 + threadIdx.x;
       }
       __syncthreads();
-      insert_slot(c, sc.mu_in, sc.mu_eq);
+      if (cnt == 1)
+        insert_slot(c, sc.mu_in, sc.mu_eq);
+      else
+        insert_block(c, cnt, sc.mu_in, sc.mu_eq);
+      if (c.overflow) break;
+      k += cnt;
     }
   }
   PROF_ADD(PH_INSERT, tp);
@@ -1752,7 +2019,7 @@ __device__ __noinline__ void global_passes(Ctx& c, bool primal, bool dual)
     __syncthreads();
     bt_dot(c, c.kt, c.kt2, v_t2, nullptr, 1.0, nullptr, v_t3);
   }
-  if (primal) axpy_pass(c, c.Bt, c.ldb, n, v_x, c.m, v_se, nullptr, 1.0); // [A x; C x] (se, rup contiguous)
+  if (primal) bt_axpy(c, v_x, v_se); // [A x; C x] (se, rup contiguous)
 }
 
 __device__ __noinline__ void global_primal_residual(Ctx& c, const Scal& sc, const pqp_settings& S, Glob& g)
