@@ -161,6 +161,27 @@ def thread_candidates():
     return sorted(c, reverse=True)
 
 
+def gpu_numa_cpus(index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None. Pinned host buffers are first-touched by this process: on
+    the pool's two-socket boxes a buffer that lands on the far socket uploads at 15-25 GB/s instead of ~50."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("00000000:"):
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if cpus else None
+    except Exception:
+        return None
+
+
 def pin_openmp_env(threads):
     """OpenMP environment of the CPU arm, set BEFORE libgomp is loaded (it reads the environment once): one thread per
     logical CPU, no migration, spinning workers. torchrun / the driver may export OMP_NUM_THREADS=1; the CPU arm must not
@@ -293,7 +314,11 @@ def main():
 
     B = args.batch
     n, ne, ni = N_DIM, N_EQ, N_IN
-    # synthetic inputs of this rank (seeds rank*B .. rank*B+B-1), in pinned host memory
+    # synthetic inputs of this rank (seeds rank*B .. rank*B+B-1), in pinned host memory allocated on the GPU's NUMA node
+    full_mask = os.sched_getaffinity(0)
+    numa = None if os.environ.get("BENCH_NO_NUMA") == "1" else gpu_numa_cpus(local_rank)  # (BENCH_NO_NUMA=1: A/B hook)
+    if numa:
+        os.sched_setaffinity(0, numa[1])
     host = generate(rank * B, B, proxqp.dense.random_qp)
     pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
     host = {k: v.numpy() for k, v in pinned.items()}
@@ -386,6 +411,7 @@ def main():
         cpu = None
         b_alg = None
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, full_mask)  # the CPU leg gets every CPU of the box again
             pin_openmp_env(host_threads())
             cpu = cpu_baseline(sample=CPU_SAMPLE, reps=5)
             b_alg = algorithmic_bytes_per_qp(cpu["counters"], n, ne, ni, ni, cpu["sample"])
@@ -425,6 +451,7 @@ def main():
             "config": {"workload": f"BatchQP {B} random dense QPs per GPU, n={n} n_eq={n_eq_str()} n_in={ni}, fp64, eps_abs=1e-9 eps_rel=0 NO_INITIAL_GUESS (BASELINE.json configs[1]'s QP shape at the north-star batch of 4096; generator of benchmark/timings-parallel.cpp)",
                        "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"batch sharded over {world} GPU(s), no collective in the iteration",
                        "e2e_mode": os.environ.get("PQP_E2E", "fused") + " (init uploads, the solve kernel equilibrates + solves each QP as its inputs arrive)",
+                       "host_buffers": "pinned, first-touched on the GPU's NUMA node %s" % (numa[0] if numa else "(unknown: default placement)"),
                        "l2": "inputs larger than L2 (scaled+model data %.0f MB per GPU per step)" % (2 * h2d_bytes / 1e6)},
             "e2e": {"value": e2e_value, "unit": "QPs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches),

@@ -109,6 +109,7 @@ def lib():
     L.pqp_batch_debug_trace.argtypes = [vp, vp, i64]
     L.pqp_batch_launch_config.argtypes = [vp, vp, vp, vp, vp]
     L.pqp_batch_profile.argtypes = [vp, vp, C.c_int]
+    L.pqp_batch_occupancy.argtypes = [vp, C.c_int]
     L.pqp_random_qp.argtypes = [C.c_int, C.c_uint64, i64, i64, i64, dbl, dbl] + [vp] * 9
     L.pqp_sharded_create.restype = vp
     L.pqp_sharded_create.argtypes = [i64, i64, i64, i64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]

@@ -214,7 +214,7 @@ fill_layout(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, bool want_m1, 
   sz[PA_VEC] = L.vec_doubles;
   const int64_t nlist = std::max(nc, cap);
   L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);
-  const int64_t budget = budget_bytes - 1024 /*static shared memory*/ - L.smem_int_bytes;
+  const int64_t budget = budget_bytes - 1664 /*static shared memory of the kernel (general kernels: 1568 B in the fused instantiation); the budget must hold for the FUSED instantiation too: round 2 found it running at one CTA per SM, 16 bytes over half an SM*/ - L.smem_int_bytes;
   int64_t smem_d = 0, ws_d = 0;
   auto put = [&](int id, bool want_smem) {
     if (want_smem && (smem_d + sz[id]) * 8 <= budget) {
@@ -308,7 +308,7 @@ fill_layout_tile(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int si_ca
   sz[PA_VEC] = L.vec_doubles;
   const int64_t nlist = std::max(nc, cap);
   L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);
-  const int64_t budget = budget_bytes - 1024 /*static shared memory*/ - L.smem_int_bytes;
+  const int64_t budget = budget_bytes - 1664 /*static shared memory of the kernel (tile kernel: 736 B plain, 1616 B in the fused instantiation); the budget must hold for the FUSED instantiation too: round 2 found it running at one CTA per SM, 16 bytes over half an SM*/ - L.smem_int_bytes;
   int64_t smem_d = 0, ws_d = 0;
   auto put = [&](int id, bool want_smem) {
     if (want_smem && (smem_d + sz[id]) * 8 <= budget) {
@@ -391,7 +391,7 @@ fill_layout_big(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int ctas)
   sz[PA_VEC] = L.vec_doubles;
   const int64_t nlist = std::max(nc, cap);
   L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);
-  const int64_t budget = budget_bytes - 1024 /*static shared memory*/ - L.smem_int_bytes;
+  const int64_t budget = budget_bytes - 2688 /*static shared memory of the kernel (big variant: 1760 B plain, 2640 B fused); the budget must hold for the FUSED instantiation too: round 2 found it running at one CTA per SM, 16 bytes over half an SM*/ - L.smem_int_bytes;
   if (sm * 8 > budget) return 1; // not even the scratch fits
   int64_t smem_d = sm, ws_d = 0;
   if ((smem_d + sz[PA_VEC]) * 8 <= budget) {
@@ -1678,6 +1678,18 @@ pqp_batch_cleanup(pqp_batch* b, int64_t first, int64_t count)
     b->flags[i].is_initialized = had_model;
   }
   return 0;
+}
+
+// test / diagnostic hook (not in pqp.h): resident CTAs per SM of the primary layout's solve kernel, plain or fused
+int
+pqp_batch_occupancy(pqp_batch* b, int fused)
+{
+  if (!b) return -1;
+  cudaSetDevice(b->device);
+  PqpSolveArgs a{};
+  a.d = b->d;
+  a.lay = b->lay;
+  return pqp_solve_occupancy(&a, fused);
 }
 
 int

@@ -155,6 +155,7 @@ extern "C" {
 // host-side launchers implemented in pqp_kernels.cu
 int pqp_launch_setup(const PqpSetupArgs* a, void* stream);
 int pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream);
+int pqp_solve_occupancy(const PqpSolveArgs* a, int fused);
 int pqp_launch_backward(const PqpSolveArgs* a, const PqpBackwardArgs* k, int grid, void* stream);
 int pqp_solve_max_smem(void);
 int64_t pqp_setup_smem_bytes(int n, int ne, int ni, int nc);

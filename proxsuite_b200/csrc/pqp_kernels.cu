@@ -691,6 +691,28 @@ pqp_launch_backward(const PqpSolveArgs* a, const PqpBackwardArgs* k, int grid, v
   return (int)cudaGetLastError();
 }
 
+// Resident CTAs per SM the runtime grants the solve kernel this layout selects (plain or fused instantiation): the
+// layout budgets of pqp_capi.cu count on two; a kernel whose static shared memory pushes it 16 bytes over half an SM
+// silently runs at one (round 2: the fused tile kernel did, 56 ms instead of 36 per 4096 QPs).
+extern "C" int
+pqp_solve_occupancy(const PqpSolveArgs* a, int fused)
+{
+#ifdef PQP_CPU_EMU
+  (void)fused;
+  return a->lay.ctas_per_sm;
+#else
+  size_t smem = sizeof(double) * (size_t)a->lay.smem_doubles + (size_t)a->lay.smem_int_bytes;
+  const int64_t symn = (int64_t)a->d.n * (a->d.n + 1) / 2, symc = (int64_t)a->lay.si_cap * (a->lay.si_cap + 1) / 2;
+  const bool fast = a->lay.in_smem[PA_VEC] && a->lay.in_smem[PA_MS] && (a->lay.in_smem[PA_M1] || a->d.hess != PQP_HESSIAN_DENSE || symn <= symc);
+  auto kern = fused ? ((a->lay.kind == 1) ? tilek::pqp_solve_kernel_fused : (a->lay.kind == 2) ? bigk::pqp_solve_kernel_fused : (fast ? fastk::pqp_solve_kernel_fused : genk::pqp_solve_kernel_fused))
+                    : ((a->lay.kind == 1) ? tilek::pqp_solve_kernel : (a->lay.kind == 2) ? bigk::pqp_solve_kernel : (fast ? fastk::pqp_solve_kernel : genk::pqp_solve_kernel));
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, smem) != cudaSuccess) return -1;
+  return nb;
+#endif
+}
+
 extern "C" int
 pqp_launch_solve(const PqpSolveArgs* a, int grid, void* stream)
 {

@@ -624,6 +624,10 @@ class DenseBatch:
     PROFILE_PHASES = ["stage", "build_M1", "eq_block", "insert", "delete", "solve_kkt", "kkt_residual", "linesearch",
                       "mu_update", "global_residuals", "newton_misc", "total"]
 
+    def occupancy(self, fused=False):
+        """resident CTAs per SM the runtime grants the solve kernel of this batch's layout (plain / fused instantiation)"""
+        return int(self._g.lib.pqp_batch_occupancy(self._g.handle, int(bool(fused))))
+
     def profile(self, reset=True):
         """Per-phase SM cycles summed over all QPs solved so far (PQP_PROFILE=1)."""
         out = (ct.c_longlong * 12)()

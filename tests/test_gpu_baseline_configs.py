@@ -294,3 +294,13 @@ def test_big_variant_of_the_tile_body(px, oracle, monkeypatch, kind, n, ne, ni, 
             assert np.abs(r.x - ro.x).max() <= XTOL * max(1.0, np.abs(ro.x).max())
             if exact:
                 assert (r.info.iter, r.info.iter_ext, r.info.mu_updates) == (ro.info.iter, ro.info.iter_ext, ro.info.mu_updates)
+
+
+def test_solve_kernels_get_the_occupancy_their_layout_counts_on(px):
+    """The layouts are sized for two CTAs per SM; the runtime must agree for BOTH instantiations of the kernel
+    (round 2: the fused tile kernel, 880 bytes more static shared memory than the plain one, ended up 16 bytes over
+    half an SM and silently ran at one CTA per SM - the end-to-end path lost 40 %)."""
+    for args in ((4, 100, 50, 100, False, px.HessianType.Dense), (4, 100, 50, 50, True, px.HessianType.Dense),
+                 (4, 256, 128, 256, False, px.HessianType.Dense), (4, 500, 250, 250, True, px.HessianType.Diagonal)):
+        db = px.dense.DenseBatch(*args[:4], box_constraints=args[4], hessian_type=args[5])
+        assert db.occupancy(False) >= 2 and db.occupancy(True) >= 2, (args[1:4], db.occupancy(False), db.occupancy(True), db.launch_config())
