@@ -385,9 +385,12 @@ fill_layout_big(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int ctas)
   int64_t sz[PA_COUNT];
   sz[PA_M1] = (d.hess == PQP_HESSIAN_DENSE) ? rnd((int64_t)n * ldn + 4) : 2;
   sz[PA_AS] = rnd((int64_t)n * ldb + 4);                 // Bt
-  sz[PA_MS] = rnd((int64_t)ord * (ord + 1) / 2 + 4);     // packed S^-1 (and P during its inversion)
+  // packed S^-1 (and P during its inversion); sized for the fallback's K^-1 of order n + capacity (pqp_fast_body.inl, kkt_factor)
+  const int64_t ordk = (int64_t)n + cap;
+  sz[PA_MS] = rnd(std::max<int64_t>((int64_t)ord * (ord + 1) / 2, ordk * (ordk + 1) / 2) + 4);
   sz[PA_G] = rnd((int64_t)m * ldb + 4);                  // G, full square (lower block triangle used)
-  sz[PA_Y] = rnd((int64_t)n * ldb + 4);                  // W
+  // W; later the fallback's panels (8), right-hand side, solution and NW partial vectors of length n + capacity
+  sz[PA_Y] = rnd(std::max<int64_t>((int64_t)n * ldb, (int64_t)(8 + 2 + PQP_NW) * ((ordk + 2) & ~int64_t(1))) + 4);
   sz[PA_VEC] = L.vec_doubles;
   const int64_t nlist = std::max(nc, cap);
   L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);
@@ -832,6 +835,7 @@ enqueue_solve(pqp_batch* b, cudaStream_t st, const PqpLayout& lay, int grid, int
   a.prof = b->prof;
   if (const char* e = std::getenv("PQP_DEBUG_TRACE")) a.dbg_qp = std::atoi(e);
   if (const char* e = std::getenv("PQP_WATCHDOG_MS")) a.watchdog_ns = 1000000ull * (unsigned long long)std::atoll(e);
+  if (const char* e = std::getenv("PQP_FORCE_KKT")) a.force_kkt = std::atoi(e);
   a.fused_setup = fused_code;
   a.ready = ready;
   {

@@ -121,6 +121,7 @@ struct PqpSolveArgs
   int32_t dbg_qp;
   int32_t dbg_cap;
   long long* prof;   // optional per-phase cycle counters (12 entries), NULL = off
+  int32_t force_kkt;  // test hook (PQP_FORCE_KKT=1): the big variant solves every QP through the whole-KKT inverse fallback
   unsigned long long watchdog_ns; // 0 = off; per-QP time budget after which the QP is abandoned (status MAX_ITER_REACHED)
   // Fused feed (end-to-end path: init() from host buffers directly followed by solve()):
   int32_t* ready;      // NULL: every input is resident. Else ready[0] = number of QPs of this launch whose inputs have

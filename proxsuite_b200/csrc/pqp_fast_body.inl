@@ -42,6 +42,10 @@ struct Ctx
   int uv_ld;       // leading dimension of the 8 sweep panel vectors kept in `scratch`
   int si_valid;    // 0: the dual block has not been formed yet (deferred to the first active-set change)
   int overflow;    // set when an insertion would exceed si_cap (QP is retried by the generic kernel)
+  // BIG variant, last-resort fallback: explicit inverse of the WHOLE KKT matrix (see kkt_factor)
+  int kkt_mode;    // 1: the dual-block path stagnated on this QP; solves go through K^-1 (stored where S^-1 was)
+  int kkt_dirty;   // K^-1 must be re-formed before the next solve (active set / mu changed)
+  double* kws;     // workspace of the fallback (the W region: free once G is built)
 };
 
 // local (register) copies of the vector pointers with the address-space hint
@@ -1097,6 +1101,28 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
 __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (c.kkt_mode) { // fallback: the panel vectors are in the global workspace (order n + n_slots does not fit shared memory)
+    _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
+      double* row = T + ts_idx(0, i, 0);
+      const double u0 = U[i], u1 = U[ldv + i], u2 = U[2 * ldv + i], u3 = U[3 * ldv + i];
+      _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 128) {
+        double a[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j0 + 32 * q;
+          a[q] = (j <= i) ? row[j] : 0.0;
+        }
+        PQP_LOADS_FIRST();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j0 + 32 * q;
+          if (j <= i) row[j] = fma(u3, V[3 * ldv + j], fma(u2, V[2 * ldv + j], fma(u1, V[ldv + j], fma(u0, V[j], a[q]))));
+        }
+      }
+    }
+    __syncthreads();
+    return;
+  }
   PQP_IN_SMEM(U); // the sweep's panel vectors live in c.scratch: shared memory in every layout of this variant
   PQP_IN_SMEM(V);
   _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
@@ -1271,14 +1297,99 @@ __device__ __forceinline__ void bt_axpy(const Ctx& c, const double* coef, double
   axpy_pass(c, c.Bt, c.ldb, c.n, coef, c.m, out, nullptr, 1.0);
 }
 
+#ifdef PQP_BIG
+// ---------------------------------------------------------------------------
+// Last-resort fallback of the BIG variant: the explicit inverse of the WHOLE regularised KKT matrix
+//   K = [ H_s + rho I   B^T ;  B   -Dlt ]   (order n + n_slots, quasi-definite: every pivot of the sweep is non-zero),
+// re-formed from scratch by the blocked sweep whenever the active set or mu changed. The block elimination through
+// S = Dlt + B P^-1 B^T squares the conditioning (cond S ~ 1e13-1e15 on the degenerate LP-like Maros-Meszaros problems,
+// cond K ~ 1e7): there the S^-1 path needs ten refinement rounds per digit and stagnates, while K^-1 gains 2-4 digits
+// per round (numpy prototype on QSCORPIO). It costs a sweep over (n + n_s)^2 / 2 elements per active-set change, so a
+// QP only switches to it when iterative_solve has failed even after re-forming the dual block.
+// Storage: K^-1 replaces S^-1 (the region is sized for order n + capacity); panels, partial sums, right-hand side and
+// solution live in the W region of the workspace (free once G is built).
+// ---------------------------------------------------------------------------
+__device__ __noinline__ void kkt_factor(Ctx& c, double rho, double mu_eq, double mu_in)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = c.n, ns = c.ns, m = n + ns, ne = c.ne;
+  double* const K = c.Si;
+  for (int i = warp; i < n; i += NW) {
+    double* row = K + ts_idx(0, i, 0);
+    const double* h = c.Hs + (size_t)i * n;
+    for (int j = lane; j <= i; j += 32) {
+      double v = (c.hess == PQP_HESSIAN_DENSE) ? h[j] : ((c.hess == PQP_HESSIAN_DIAGONAL && j == i) ? h[j] : 0.0);
+      row[j] = v + ((j == i) ? rho : 0.0);
+    }
+  }
+  for (int sl = warp; sl < ns; sl += NW) {
+    const int id = row_id(c, sl);
+    double* row = K + ts_idx(0, n + sl, 0);
+    for (int j = lane; j < n; j += 32) row[j] = c.Bt[(size_t)j * c.ldb + id];
+    for (int t = lane; t <= sl; t += 32) row[n + t] = (t == sl) ? -(sl < ne ? mu_eq : mu_in) : 0.0;
+  }
+  __syncthreads();
+  const int ldk = (n + c.cap + 2) & ~1;
+  tsym_sweep_invert(c, K, c.kws, ldk, m); // panels: 8 x ldk doubles at the start of the fallback workspace
+  if (threadIdx.x == 0) c.kkt_dirty = 0;
+  __syncthreads();
+}
+
+__device__ __noinline__ void kkt_solve(Ctx& c, const double* b1, const double* b2, double* ox, double* os)
+{
+  PQP_VECS(c);
+  const int n = c.n, ns = c.ns, m = n + ns, ne = c.ne;
+  const int ldk = (n + c.cap + 2) & ~1;
+  double* const r = c.kws + (size_t)8 * ldk;   // right-hand side
+  double* const y = r + ldk;                   // solution
+  double* const part = y + ldk;                // NW x m partial vectors of the symmetric mat-vec
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) r[j] = b1[j];
+  _Pragma("unroll 1") for (int t = threadIdx.x; t < ns; t += NT) r[n + t] = b2[t];
+  double* const saved = c.scratch;
+  __syncthreads();
+  if (threadIdx.x == 0) c.scratch = part;
+  __syncthreads();
+  tsym_mv(c, c.Si, r, y, m);
+  if (threadIdx.x == 0) c.scratch = saved;
+  __syncthreads();
+  _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) ox[j] = y[j];
+  _Pragma("unroll 1") for (int t = threadIdx.x; t < ns; t += NT) os[t] = y[n + t];
+  __syncthreads();
+  // B^T lam for kkt_residual (v_ctdz), as the dual-block path leaves it
+  _Pragma("unroll 1") for (int id = threadIdx.x; id < c.ldb; id += NT) {
+    double lam = 0.0;
+    if (id < ne) {
+      lam = os[id];
+    } else if (id < c.m) {
+      const int sl = c.cons_slot[id - ne];
+      if (sl >= 0) lam = os[sl];
+    }
+    c.kt[id] = lam;
+  }
+  __syncthreads();
+  bt_dot(c, c.kt, nullptr, v_t2, nullptr, 1.0, v_ctdz, nullptr);
+}
+#endif
+
 // Solve K [ox; os] = [b1; b2],  K = [P B^T; B -Dlt], with the explicit block
 // inverses:  t = P^-1 b1;  lam = S^-1 (B t - b2);  x = P^-1 (b1 - B^T lam).
 // In place allowed (ox == b1, os == b2). Replaces Ldlt::solve_in_place
 // (ldlt.hpp:767-782).
-__device__ __noinline__ void solve_kkt(const Ctx& c, const double* b1, const double* b2, double* ox, double* os)
+__device__ __noinline__ void solve_kkt(Ctx& c, const double* b1, const double* b2, double* ox, double* os, double rho, double mu_eq, double mu_in)
 {
   PQP_VECS(c);
   const int ns = c.ns, n = c.n, ne = c.ne;
+#ifdef PQP_BIG
+  if (c.kkt_mode) { // block-uniform: written by thread 0 behind a barrier
+    if (c.kkt_dirty) kkt_factor(c, rho, mu_eq, mu_in);
+    kkt_solve(c, b1, b2, ox, os);
+    return;
+  }
+#else
+  (void)rho;
+  (void)mu_eq;
+  (void)mu_in;
+#endif
   if (ns == 0) {
     apply_Pinv(c, b1, v_t1);
     _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
@@ -1322,6 +1433,17 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu, double mu_eq)
   PQP_VECS(c);
   const int s = c.ns;
   const int cap = c.si_cap;
+#ifdef PQP_BIG
+  if (c.kkt_mode) { // fallback: only the slot count moves; K^-1 is re-formed before the next solve
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      c.ns = s + 1;
+      c.kkt_dirty = 1;
+    }
+    __syncthreads();
+    return;
+  }
+#endif
   if (s + 1 > cap) { // does not fit the shared-memory S^-1: hand the QP to the generic kernel
     if (threadIdx.x == 0) c.overflow = 1;
     __syncthreads();
@@ -1384,6 +1506,17 @@ __device__ __noinline__ void insert_block(Ctx& c, int kcnt, double mu, double mu
 {
   PQP_VECS(c);
   const int s0 = c.ns, cap = c.si_cap, ldv = c.uv_ld;
+#ifdef PQP_BIG
+  if (c.kkt_mode) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      c.ns = s0 + kcnt;
+      c.kkt_dirty = 1;
+    }
+    __syncthreads();
+    return;
+  }
+#endif
   if (s0 + kcnt > cap) { // does not fit the shared-memory S^-1: hand the QP to the generic kernel
     if (threadIdx.x == 0) c.overflow = 1;
     __syncthreads();
@@ -1504,18 +1637,28 @@ __device__ __noinline__ void drop_slot(Ctx& c, int k)
   const int ns = c.ns, cap = c.si_cap, L = ns - 1;
   double* T = c.Si;
   __syncthreads();
-  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = ts_get(T, cap, i, L);
-  __syncthreads();
-  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
-    if (k != L) {
-      if (i == k)
-        T[ts_idx(cap, k, k)] = v_s1[L];
-      else if (i != L)
-        ts_put(T, cap, i, k, v_s1[i]);
+#ifdef PQP_BIG
+  const bool storage = !c.kkt_mode; // fallback: K^-1 is re-formed from scratch, only the maps move
+#else
+  const bool storage = true;
+#endif
+  if (storage) {
+    _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = ts_get(T, cap, i, L);
+    __syncthreads();
+    _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
+      if (k != L) {
+        if (i == k)
+          T[ts_idx(cap, k, k)] = v_s1[L];
+        else if (i != L)
+          ts_put(T, cap, i, k, v_s1[i]);
+      }
+      ts_put(T, cap, L, i, 0.0);
     }
-    ts_put(T, cap, L, i, 0.0);
   }
   if (threadIdx.x == 0) {
+#ifdef PQP_BIG
+    if (c.kkt_mode) c.kkt_dirty = 1;
+#endif
     const int cons_k = c.slot_cons[k], cons_L = c.slot_cons[L];
     if (k != L) {
       c.slot_cons[k] = cons_L;
@@ -1532,6 +1675,12 @@ __device__ __noinline__ void delete_slot(Ctx& c, int k)
   PQP_VECS(c);
   const int ns = c.ns, cap = c.si_cap, L = ns - 1;
   double* T = c.Si;
+#ifdef PQP_BIG
+  if (c.kkt_mode) {
+    drop_slot(c, k);
+    return;
+  }
+#endif
   _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = ts_get(T, cap, i, k);
   __syncthreads();
   const double sinv = -1.0 / v_s1[k];
@@ -1560,6 +1709,25 @@ __device__ __noinline__ void delete_block(Ctx& c, int kcnt, int k0, int k1, int 
   double* const U = v_scratch;
   double* const V = v_scratch + 4 * ldv;
   const int ks[4] = { k0, k1, k2, k3 };
+#ifdef PQP_BIG
+  if (c.kkt_mode) { // maps only, highest position first
+    int ord[4] = { k0, k1, k2, k3 };
+    for (int a = 0; a < 4; ++a) {
+      if (a >= kcnt) ord[a] = -1;
+    }
+    for (int a = 0; a < 3; ++a) {
+      for (int b = 0; b < 3 - a; ++b) {
+        if (ord[b] < ord[b + 1]) {
+          const int t = ord[b];
+          ord[b] = ord[b + 1];
+          ord[b + 1] = t;
+        }
+      }
+    }
+    for (int a = 0; a < kcnt; ++a) drop_slot(c, ord[a]);
+    return;
+  }
+#endif
   _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) V[a * ldv + i] = (a < kcnt) ? ts_get(T, cap, i, ks[a]) : 0.0;
@@ -1640,6 +1808,15 @@ __device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_i
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifdef PQP_BIG
   (void)cap;
+  if (c.kkt_mode) { // fallback: nothing to maintain here, K^-1 is re-formed before the next solve
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      c.si_valid = 1;
+      c.kkt_dirty = 1;
+    }
+    __syncthreads();
+    return;
+  }
   for (int s = warp; s < ns; s += NW) {
     const int ids = row_id(c, s);
     double* row = c.Si + ts_idx(0, s, 0);
@@ -1871,10 +2048,10 @@ __device__ void refactorize(Ctx& c, Scal& sc)
 __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_settings& S, double eps)
 {
   PQP_VECS(c);
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 3; ++pass) {
     int it = 0, it_stab = 0;
     long long tp = PROF_T0();
-    solve_kkt(c, v_rx, v_rs, v_dx, v_ds);
+    solve_kkt(c, v_rx, v_rs, v_dx, v_ds, sc.rho, sc.mu_eq, sc.mu_in);
     PROF_ADD(PH_SOLVE, tp);
     tp = PROF_T0();
     double err = kkt_residual(c, sc, true);
@@ -1893,7 +2070,7 @@ __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_setting
       if (it >= S.nb_iterative_refinement) break;
       ++it;
       tp = PROF_T0();
-      solve_kkt(c, v_ex, v_es, v_ex, v_es);
+      solve_kkt(c, v_ex, v_es, v_ex, v_es, sc.rho, sc.mu_eq, sc.mu_in);
       _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) v_dx[j] += v_ex[j];
       _Pragma("unroll 1") for (int s = threadIdx.x; s < c.ns; s += NT) v_ds[s] += v_es[s];
       __syncthreads();
@@ -1913,6 +2090,19 @@ __device__ __noinline__ void iterative_solve(Ctx& c, Scal& sc, const pqp_setting
       refactorize(c, sc);
       continue;
     }
+#ifdef PQP_BIG
+    // still not solved with a freshly re-formed dual block: this QP is beyond the S^-1 path (see kkt_factor); the rest
+    // of it is solved through the inverse of the whole KKT matrix (err is block-uniform: it comes out of a reduction)
+    if (pass <= 1 && err >= fmax(eps, S.eps_refact) && !c.kkt_mode) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        c.kkt_mode = 1;
+        c.kkt_dirty = 1;
+      }
+      __syncthreads();
+      continue;
+    }
+#endif
     break;
   }
   _Pragma("unroll 1") for (int j = threadIdx.x; j < c.n; j += NT) v_rx[j] = 0;
@@ -2392,6 +2582,8 @@ __device__ PQP_SOLVE_ONE_ATTR void solve_one(Ctx& c, const PqpSolveArgs& A, int 
       c.c_scale = P.c[q];
       c.ns = 0;
       c.overflow = 0;
+      c.kkt_mode = A.force_kkt ? 1 : 0;
+      c.kkt_dirty = c.kkt_mode;
     }
     __syncthreads();
   }
@@ -3012,7 +3204,10 @@ __device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A)
     c.kt = smem_dyn + L.voff[V_KT];
     c.kt2 = c.alphas; // shares the line-search breakpoint array (never live together)
     c.vec_smem = L.in_smem[PA_VEC];
+    c.kws = c.W;
 #endif
+    c.kkt_mode = 0;
+    c.kkt_dirty = 0;
     int* ib = reinterpret_cast<int*>(smem_dyn + L.smem_doubles);
     c.cons_slot = ib;
     c.slot_cons = c.cons_slot + A.d.nc;

@@ -275,7 +275,37 @@ def sharded_case():
     return ok
 
 
+def big_variant_case(force_kkt=False):
+    """BIG variant of the tile body (PQP_LAYOUT=big; with force_kkt its whole-KKT inverse fallback): the GPU tests' bodies"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("tb2", os.path.join(ROOT, "tests", "test_gpu_baseline_configs.py"))
+    tb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tb)
+
+    class MP:
+        def setenv(self, k, v):
+            os.environ[k] = v
+    ok = True
+    try:
+        if force_kkt:
+            for args in (("strongly_convex", 20, 6, 12, False, 1, 0.3), ("box_benchmark", 20, 6, 10, True, 1, 0.5), ("not_strongly_convex", 40, 20, 20, False, 1, 0.3)):
+                tb.test_whole_kkt_inverse_fallback(proxqp, O, MP(), *args)
+        else:
+            for args in (("strongly_convex", 20, 6, 12, False, 1, 0.3, True), ("box_benchmark", 20, 6, 10, True, 1, 0.5, True), ("diagonal_benchmark", 24, 6, 6, True, 2, 0.5, True)):
+                tb.test_big_variant_of_the_tile_body(proxqp, O, MP(), *args)
+    except AssertionError as e:
+        print("big variant failed:", e, flush=True)
+        ok = False
+    finally:
+        os.environ.pop("PQP_LAYOUT", None)
+        os.environ.pop("PQP_FORCE_KKT", None)
+    print(json.dumps(dict(name="big_kkt" if force_kkt else "big_variant", ok=ok)), flush=True)
+    return ok
+
+
 CASES = {
+    "big_variant": big_variant_case,
+    "big_kkt": lambda: big_variant_case(True),
     "qplayer_infeas": qplayer_infeas_case,
     "sharded": sharded_case,
     "qplayer": qplayer_case,

@@ -60,6 +60,12 @@ def test_torch_qp_layer_gradients_on_the_emulator(emu_lib):
     run_cases(emu_lib, ["qplayer", "qplayer_device_api", "qplayer_infeas"])
 
 
+def test_big_variant_and_its_kkt_fallback_on_the_emulator(emu_lib):
+    """The BIG variant of the tile body (packed storage in the workspace, block rank-4 insertion / deletion, Hessian types,
+    box rows) and its whole-KKT inverse fallback (PQP_FORCE_KKT=1): oracle parity incl. iteration counters."""
+    run_cases(emu_lib, ["big_variant", "big_kkt"])
+
+
 def test_sharded_batch_of_the_c_abi_on_the_emulator(emu_lib):
     """pqp_sharded_* (include/pqp.h): uneven slices over a device list, bit-identical to one batch; update + re-solve."""
     run_cases(emu_lib, ["sharded"])

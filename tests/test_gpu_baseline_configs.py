@@ -304,3 +304,37 @@ def test_solve_kernels_get_the_occupancy_their_layout_counts_on(px):
                  (4, 256, 128, 256, False, px.HessianType.Dense), (4, 500, 250, 250, True, px.HessianType.Diagonal)):
         db = px.dense.DenseBatch(*args[:4], box_constraints=args[4], hessian_type=args[5])
         assert db.occupancy(False) >= 2 and db.occupancy(True) >= 2, (args[1:4], db.occupancy(False), db.occupancy(True), db.launch_config())
+
+
+@pytest.mark.parametrize("kind,n,ne,ni,box,hessian,sparsity", [
+    ("strongly_convex", 20, 6, 12, False, 1, 0.3),
+    ("box_benchmark", 20, 6, 10, True, 1, 0.5),
+    ("diagonal_benchmark", 24, 6, 6, True, 2, 0.5),
+    ("not_strongly_convex", 40, 20, 20, False, 1, 0.3),
+])
+def test_whole_kkt_inverse_fallback(px, oracle, monkeypatch, kind, n, ne, ni, box, hessian, sparsity):
+    """PQP_FORCE_KKT=1 sends every QP of the big variant through its last-resort fallback from the first solve on: the
+    explicit inverse of the whole regularised KKT matrix (re-formed by the sweep whenever the active set or mu change)
+    instead of the dual-block inverse. It is as accurate as the reference's LDL^T (cond K instead of cond S ~ cond K^2), so
+    even the ill-conditioned not_strongly_convex family reproduces the oracle's iteration counters exactly."""
+    monkeypatch.setenv("PQP_LAYOUT", "big")
+    monkeypatch.setenv("PQP_FORCE_KKT", "1")
+    keys = list(KEYS) + (["l_box", "u_box"] if box else [])
+    for seed in (1, 2):
+        d = oracle.generate_qp(kind, seed, n, ne, ni, sparsity)
+        qp = px.dense.QP(n, ne, ni, box, px.HessianType(hessian))
+        qp.settings.eps_abs = EPS
+        qp.settings.eps_rel = 0
+        qp.settings.initial_guess = px.InitialGuess.NO_INITIAL_GUESS
+        qp.init(*[d[k] for k in keys])
+        qp.solve()
+        qo = oracle.OracleQP(n, ne, ni, box_constraints=box, hessian_type=hessian)
+        qo.set(eps_abs=EPS, eps_rel=0, initial_guess=oracle.NO_INITIAL_GUESS)
+        qo.init(**{k: d[k] for k in keys})
+        ro = qo.solve()
+        r = qp.results
+        assert int(r.info.status) == ro.info.status == 0
+        pri, dua = kkt_residuals(d, r.x, r.y, r.z)
+        assert pri <= EPS and dua <= EPS
+        assert np.abs(r.x - ro.x).max() <= XTOL * max(1.0, np.abs(ro.x).max())
+        assert (r.info.iter, r.info.iter_ext, r.info.mu_updates) == (ro.info.iter, ro.info.iter_ext, ro.info.mu_updates)

@@ -515,26 +515,25 @@ def test_maros_meszaros_small_problems(px, oracle):
         assert qp.results.info.iter == 0, name
 
 
-# problems of the larger set that are slow on the explicit-inverse path (thousands of Newton steps, tens of seconds on
-# one CTA) and the one it does not solve: run with PQP_TEST_SLOW=1 (tools/mm_gpu_debug.py prints all of them)
+# problems of the larger set that take tens of seconds on one CTA (thousands of Newton steps, or the whole-KKT fallback
+# with a 1100 x 1100 inverse per active-set change): run with PQP_TEST_SLOW=1 (tools/mm_gpu_debug.py prints all of them)
 MAROS_SLOW = ("QFORPLAN", "QSCAGR25")
-MAROS_UNSOLVED = ("QSCORPIO",)
 
 
 def test_maros_meszaros_rest_of_the_reference_list(px, oracle, monkeypatch):
     """The other 34 problems the reference's dense Maros-Meszaros test runs (n up to 760, up to 856 constraint rows;
     tests/golden/maros_meszaros_large.npz), through the C-ABI: status SOLVED, the reference's residual criteria,
-    the oracle's objective. Known gap, stated rather than hidden: QSCORPIO (degenerate LP-like problem, n = 358, 746
-    rows) is solved by the oracle's LDL^T in 68 Newton steps but NOT by the explicit-inverse GPU path (it keeps
-    re-forming the dual block and has not converged after minutes; the per-QP watchdog turns that into
-    MAX_ITER_REACHED); QFORPLAN / QSCAGR25 are solved but need 1.5x / 19x the oracle's Newton steps."""
+    the oracle's objective. With the 28 small ones: every problem the reference's test does not skip. QSCORPIO (degenerate,
+    n = 358, 746 rows) and QSCAGR25 are the two the dual-block inverse cannot handle (cond S ~ 1e13-1e15): the big variant
+    switches them to the inverse of the whole KKT matrix on its own and then needs the oracle's Newton steps (69 vs 68,
+    488 vs 489)."""
     from test_oracle_maros import EPS as MEPS, check_reference_criteria, problems_large
 
     slow = os.environ.get("PQP_TEST_SLOW") == "1"
     monkeypatch.setenv("PQP_WATCHDOG_MS", "120000" if slow else "30000")
     done = 0
     for name, d in problems_large():
-        if not slow and (name in MAROS_SLOW or name in MAROS_UNSOLVED):
+        if not slow and name in MAROS_SLOW:
             continue
         n, ne, ni = d["H"].shape[0], d["A"].shape[0], d["C"].shape[0]
         qo = oracle.OracleQP(n, ne, ni, dense_backend=oracle.BACKEND_AUTOMATIC)
@@ -549,15 +548,12 @@ def test_maros_meszaros_rest_of_the_reference_list(px, oracle, monkeypatch):
         qp.init(d["H"], d["g"], d["A"], d["b"], d["C"], d["l"], d["u"])
         qp.solve()
         r = qp.results
-        if name in MAROS_UNSOLVED:
-            assert ro.info.status == 0 and int(r.info.status) != 0, name  # the day this fails the gap is closed
-            continue
         assert int(r.info.status) == ro.info.status == 0, (name, int(r.info.status), r.info.iter)
         check_reference_criteria(d, r.x, r.y, r.z)
         obj_o = 0.5 * ro.x @ d["H"] @ ro.x + d["g"] @ ro.x
         assert abs(r.info.objValue - obj_o) <= 1e-5 * max(1.0, abs(obj_o)), name
         done += 1
-    assert done == (33 if slow else 31)
+    assert done == (34 if slow else 32)
 
 
 @pytest.mark.gpu

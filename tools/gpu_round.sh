@@ -8,12 +8,13 @@ nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/gpu
 echo "== pytest"; timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
 echo "== stress"; timeout 200 python tools/stress_launch.py 30 1 2>&1 | tail -1 | tee gpurun_out/stress.log
 echo "== bench"; timeout 400 python bench.py 2>gpurun_out/bench_err.log | tee gpurun_out/bench.json; tail -2 gpurun_out/bench_err.log
-echo "== bench reference arm"; timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tee gpurun_out/bench_ref.json
-echo "== ncu launch list"; timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -1 gpurun_out/ncu_bench.log | cut -c1-160
+echo "== bench reference arm"; timeout 300 python bench.py --impl reference --steps 5 --warmup 3 2>/dev/null | tee gpurun_out/bench_ref.json
+echo "== ncu launch list"; timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -1 gpurun_out/ncu_bench.log | cut -c1-160
 echo "== sanitizers (tile / general / big kernels, small shapes)"
 timeout 400 compute-sanitizer --tool racecheck --racecheck-report analysis python tools/sanitize_target.py 2>&1 | tail -2 | tee gpurun_out/racecheck.log
 PQP_LAYOUT=big timeout 400 compute-sanitizer --tool racecheck --racecheck-report analysis python tools/sanitize_target.py 2>&1 | tail -2 | tee -a gpurun_out/racecheck.log
+PQP_LAYOUT=big timeout 400 compute-sanitizer --tool memcheck python tools/sanitize_target.py 2>&1 | tail -1 | tee gpurun_out/memcheck_big.log
 timeout 400 compute-sanitizer --tool synccheck python tools/sanitize_target.py 2>&1 | tail -1 | tee gpurun_out/synccheck.log
 if [ "${NCU_FULL:-1}" = "1" ]; then
-  echo "== ncu --set full (plain solve kernel)"; PQP_E2E=plain timeout 400 ncu --set full --clock-control none --import-source on -k regex:pqp_solve_kernel -c 1 -f -o gpurun_out/solve_full python tools/ncu_target.py 592 1 2>&1 | tail -2
+  echo "== ncu --set full (plain solve kernel)"; PQP_E2E=plain timeout 900 ncu --set full --clock-control none --import-source on -k regex:pqp_solve_kernel -c 1 -f -o gpurun_out/solve_full python tools/ncu_target.py 4096 1 2>&1 | tail -2
 fi
