@@ -1401,6 +1401,16 @@ pqp_batch_sync(pqp_batch* b)
   CUDA_TRY(cudaSetDevice(b->device));
   CUDA_TRY(cudaStreamSynchronize(b->stream));
   CUDA_TRY(cudaDeviceSynchronize());
+  if (b->solve_pending && b->d_ready) {
+    // fused feed: a CTA that waited 20 s for its QP's inputs raised the abort flag and the rest of the batch was left
+    // NOT_RUN - that must not look like a successful solve
+    int32_t flag[2] = { 0, 0 };
+    CUDA_TRY(cudaMemcpy(flag, b->d_ready, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag[1] != 0) {
+      b->solve_pending = false;
+      return fail(PQP_ECUDA, "fused feed aborted: the inputs of a QP did not arrive within 20 s (status NOT_RUN on the affected QPs)");
+    }
+  }
   if (b->solve_pending) {
     std::vector<double> raw((size_t)b->B * PQP_INFO_DOUBLES);
     CUDA_TRY(cudaMemcpy(raw.data(), b->p.info, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost));
