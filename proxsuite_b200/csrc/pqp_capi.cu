@@ -394,7 +394,7 @@ fill_layout_big(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int ctas)
   sz[PA_VEC] = L.vec_doubles;
   const int64_t nlist = std::max(nc, cap);
   L.smem_int_bytes = (int32_t)((4 * (nc + cap + nlist + nc + 2 * PQP_NW + 8) + 2 * nc + 15) & ~15);
-  const int64_t budget = budget_bytes - 2688 /*static shared memory of the kernel (big variant: 1760 B plain, 2640 B fused); the budget must hold for the FUSED instantiation too: round 2 found it running at one CTA per SM, 16 bytes over half an SM*/ - L.smem_int_bytes;
+  const int64_t budget = budget_bytes - 1664 /*static shared memory of the kernel (752 B plain, 1632 B in the fused instantiation; cuobjdump's SHARED figure adds the 1 KB system reserve); the budget must hold for the FUSED instantiation too: round 2 found it running at one CTA per SM, 16 bytes over half an SM*/ - L.smem_int_bytes;
   if (sm * 8 > budget) return 1; // not even the scratch fits
   int64_t smem_d = sm, ws_d = 0;
   if ((smem_d + sz[PA_VEC]) * 8 <= budget) {
@@ -482,6 +482,15 @@ make_layout(pqp_batch* b)
     PqpLayout two, one;
     const int r2 = fill_layout_big(d, two, half, 2);           // 0: the shared-memory scratch part fits twice per SM
     const int r1 = fill_layout_big(d, one, (int64_t)max_smem, 1);
+    if (const char* e3 = std::getenv("PQP_BIG_CTAS")) { // experiment hook: three CTAs per SM (needs a build with -DPQP_BIG_CTAS3)
+      PqpLayout three;
+      if (std::atoi(e3) == 3 && fill_layout_big(d, three, ((int64_t)smem_sm - 3 * 1024) / 3, 3) == 0 && three.in_smem[PA_VEC]) {
+        b->lay = three;
+        done = true;
+      }
+    }
+    if (done) {
+    } else
     // two CTAs per SM when the vector arena fits in half an SM as well - or when it would not fit in a whole one either
     if (r2 == 0 && (two.in_smem[PA_VEC] || r1 != 0 || !one.in_smem[PA_VEC])) {
       b->lay = two;
