@@ -482,15 +482,7 @@ make_layout(pqp_batch* b)
     PqpLayout two, one;
     const int r2 = fill_layout_big(d, two, half, 2);           // 0: the shared-memory scratch part fits twice per SM
     const int r1 = fill_layout_big(d, one, (int64_t)max_smem, 1);
-    if (const char* e3 = std::getenv("PQP_BIG_CTAS")) { // experiment hook: three CTAs per SM (needs a build with -DPQP_BIG_CTAS3)
-      PqpLayout three;
-      if (std::atoi(e3) == 3 && fill_layout_big(d, three, ((int64_t)smem_sm - 3 * 1024) / 3, 3) == 0 && three.in_smem[PA_VEC]) {
-        b->lay = three;
-        done = true;
-      }
-    }
-    if (done) {
-    } else
+
     // two CTAs per SM when the vector arena fits in half an SM as well - or when it would not fit in a whole one either
     if (r2 == 0 && (two.in_smem[PA_VEC] || r1 != 0 || !one.in_smem[PA_VEC])) {
       b->lay = two;

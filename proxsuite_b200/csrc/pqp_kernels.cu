@@ -68,17 +68,9 @@ namespace tilek {
 // dense / diagonal / zero Hessian, box constraints. Serves the shapes the tile kernel proper cannot hold in shared
 // memory (BASELINE cfg 3: dual block 200; cfg 4: n = 256; cfg 5: n = 500, diagonal Hessian, 1000 rows).
 #define PQP_BIG 1
-#ifdef PQP_BIG_CTAS3 // experiment: register budget for three CTAs per SM (85 registers per thread)
-#undef PQP_MIN_CTAS
-#define PQP_MIN_CTAS 3
-#endif
 namespace bigk {
 #include "pqp_fast_body.inl"
 }
-#ifdef PQP_BIG_CTAS3
-#undef PQP_MIN_CTAS
-#define PQP_MIN_CTAS 2
-#endif
 #undef PQP_BIG
 #define PQP_WITH_BACKWARD 1
 namespace genk {
