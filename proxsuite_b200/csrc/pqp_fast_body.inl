@@ -698,7 +698,10 @@ __device__ __forceinline__ int ts_extent(int cap, int n)
 }
 
 // y = T x (order n). x and y must not alias. Uses c.scratch (NW x 128).
-__device__ __noinline__ void tsym_mv(const Ctx& c, const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n)
+// want_dot: also returns x . y (block-uniform), reduced in the same final phase: the partial products ride on the
+// combination loop, one barrier publishes the warp sums, and there is NO trailing barrier - the caller must pass one
+// before c.red is written again (insert_slot: the barrier ahead of the rank-1 update).
+__device__ __noinline__ double tsym_mv(const Ctx& c, const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n, bool want_dot = false)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cap = c.si_cap;
@@ -744,13 +747,27 @@ __device__ __noinline__ void tsym_mv(const Ctx& c, const double* __restrict__ T,
     if (b < nb) scr[warp * 128 + 32 * b + lane] = acc[b];
   }
   __syncthreads();
+  double part = 0.0;
   _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) s += scr[w * 128 + j];
     y[j] = s;
+    if (want_dot) part += x[j] * s;
+  }
+  if (want_dot) { // block-uniform
+    double* const red = c.red;
+    PQP_SM(red);
+    part = warp_sum(part);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    double d = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) d += red[w];
+    return d;
   }
   __syncthreads();
+  return 0.0;
 }
 
 // T[i][j] += u_i v_j on every stored element with i, j < n (u, v in shared memory).
@@ -1012,7 +1029,8 @@ __device__ __forceinline__ int ts_extent(int, int n)
 //   y_i = sum_{j <= i} T[i][j] x_j  (row part: a warp owns row i, coalesced loads, one warp reduction)
 //       + sum_{i' > i} T[i'][i] x_i' (column part, AXPY form: lane-stationary accumulators for a group of 256 columns)
 // Row i belongs to the same lane-0 thread in every column group (256 is a multiple of NW): fixed summation order.
-__device__ __noinline__ void tsym_mv(const Ctx& c, const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n)
+// want_dot: as in the tile version (x . y comes out of the final phase, no trailing barrier).
+__device__ __noinline__ double tsym_mv(const Ctx& c, const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n, bool want_dot = false)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* const scr = c.scratch;
@@ -1060,13 +1078,25 @@ __device__ __noinline__ void tsym_mv(const Ctx& c, const double* __restrict__ T,
     }
   }
   __syncthreads();
+  double part = 0.0;
   _Pragma("unroll 1") for (int j = threadIdx.x; j < n; j += NT) {
     double sacc = y[j];
 #pragma unroll
     for (int w = 0; w < NW; ++w) sacc += scr[(size_t)w * n + j];
     y[j] = sacc;
+    if (want_dot) part += x[j] * sacc;
+  }
+  if (want_dot) { // block-uniform
+    part = warp_sum(part);
+    if (lane == 0) c.red[warp] = part;
+    __syncthreads();
+    double d = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) d += c.red[w];
+    return d;
   }
   __syncthreads();
+  return 0.0;
 }
 
 // T[i][j] += u_i v_j on the packed lower triangle (j <= i < n). Eight independent read-modify-writes per lane are in
@@ -1428,11 +1458,18 @@ __device__ __noinline__ void solve_kkt(Ctx& c, const double* b1, const double* b
 //   S^-1 <- [S^-1 + w w^T/delta, -w/delta; -w^T/delta, 1/delta].
 // Replaces Ldlt::insert_block_at (ldlt.hpp:431-475, modify.hpp:131-264).
 __device__ __noinline__ void rebuild_Si_from_G(Ctx& c, double mu_eq, double mu_in);
-__device__ __noinline__ void insert_slot(Ctx& c, double mu, double mu_eq)
+// Inequality row `cons` enters as dual slot c.ns. The caller guarantees that every thread is past the previous
+// barrier-terminated primitive (c.ns stable, nobody still reads the slot maps); the maps are written here, by thread 0,
+// in the phase that gathers the Gram row (which takes the new slot's row id from `cons`, not from the map).
+__device__ __noinline__ void insert_slot(Ctx& c, double mu, double mu_eq, int cons)
 {
   PQP_VECS(c);
   const int s = c.ns;
   const int cap = c.si_cap;
+  if (threadIdx.x == 0 && s + 1 <= c.cap) {
+    c.slot_cons[s] = cons;
+    c.cons_slot[cons] = s;
+  }
 #ifdef PQP_BIG
   if (c.kkt_mode) { // fallback: only the slot count moves; K^-1 is re-formed before the next solve
     __syncthreads();
@@ -1451,19 +1488,19 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu, double mu_eq)
   }
   {
     // Gram row of the new slot against slots 0..s: a gather from G
-    const int ids = row_id(c, s);
+    const int ids = c.ne + cons;
     _Pragma("unroll 1") for (int j = threadIdx.x; j <= s; j += NT) {
-      const int idj = row_id(c, j);
+      const int idj = (j == s) ? ids : row_id(c, j);
       v_s3[j] = c.G[(size_t)max(ids, idj) * c.ldb + min(ids, idj)];
     }
     __syncthreads();
   }
+  // five barriers per insertion (eight before: the kernel pays ~1.8 k cycles of dependent latency per barrier interval
+  // here, 350 of a cfg-2 QP's 1600 intervals were insertions): g.w comes out of the mat-vec's final phase, the
+  // border, the diagonal and the slot count are written in the phase that forms w / delta
   double delta = v_s3[s] + mu;
   if (s > 0) {
-    tsym_mv(c, c.Si, v_s3, v_s1, s);
-    double part = 0;
-    _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) part += v_s3[j] * v_s1[j];
-    delta -= block_sum1(c, part);
+    delta -= tsym_mv(c, c.Si, v_s3, v_s1, s, true); // w = S^-1 g in v_s1, g.w returned (no trailing barrier: see below)
     // delta = (b.P^-1 b + mu) - g.w is the Schur complement of the new slot in S; it cancels when the new row is nearly
     // dependent on the active ones (terms ~ |b|^2 / rho against mu). A non-positive or fully cancelled value means
     // the bordering formula has no accuracy left: register the slot and re-form S^-1 from the Gram matrix instead
@@ -1476,19 +1513,18 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu, double mu_eq)
       return;
     }
     const double dinv = 1.0 / delta;
-    _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) {
+    _Pragma("unroll 1") for (int j = threadIdx.x; j < s; j += NT) { // w_j was written by this very thread
       const double wj = v_s1[j] * dinv;
       v_s2[j] = wj;
       ts_put(c.Si, cap, s, j, -wj);
     }
-    __syncthreads();
-    tsym_rank1(c, c.Si, v_s1, v_s2, s);
   }
   if (threadIdx.x == 0) {
-    c.Si[ts_idx(cap, s, s)] = 1.0 / delta;
+    c.Si[ts_idx(cap, s, s)] = 1.0 / delta; // row s is outside the order-s update below
     c.ns = s + 1;
   }
-  __syncthreads();
+  __syncthreads(); // w, w / delta complete; also the barrier c.red needed after the fused reduction
+  if (s > 0) tsym_rank1(c, c.Si, v_s1, v_s2, s);
 }
 
 // Remove dual slot k (k >= ne): Schur complement of the explicit inverse,
@@ -1681,18 +1717,41 @@ __device__ __noinline__ void delete_slot(Ctx& c, int k)
     return;
   }
 #endif
-  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) v_s1[i] = ts_get(T, cap, i, k);
-  __syncthreads();
-  const double sinv = -1.0 / v_s1[k];
-  __syncthreads();
+  // Three barriers per deletion (seven before). The last slot L moves into the freed position k BEFORE the rank-1
+  // pass: its updated column p'_i = T[i][L] + q_i q_L sinv is formed explicitly (same fma as the pass would apply to the
+  // stored element (L, i)), rows / columns k of the update vectors are zero, and the pass runs on order ns - 1.
   _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
-    const double q = (i == k) ? 0.0 : v_s1[i]; // row / column k are dropped below
-    v_s2[i] = q;
-    v_s3[i] = q * sinv;
+    v_s1[i] = ts_get(T, cap, i, k); // q: column k
+    v_s2[i] = ts_get(T, cap, i, L); // p: column of the last slot
   }
   __syncthreads();
-  tsym_rank1(c, T, v_s2, v_s3, ns);
-  drop_slot(c, k);
+  const double sinv = -1.0 / v_s1[k];
+  const double qL = (k == L) ? 0.0 : v_s1[L];
+  _Pragma("unroll 1") for (int i = threadIdx.x; i < ns; i += NT) {
+    const double q = (i == k) ? 0.0 : v_s1[i]; // row / column k are dropped
+    const double v = q * sinv;
+    const double pp = fma(qL, v, v_s2[i]);     // element (L, i) after the update
+    v_s2[i] = q;
+    v_s3[i] = v;
+    if (k != L) {
+      if (i == L)
+        T[ts_idx(cap, k, k)] = pp;
+      else if (i != k)
+        ts_put(T, cap, i, k, pp);
+    }
+    ts_put(T, cap, L, i, 0.0);
+  }
+  if (threadIdx.x == 0) {
+    const int cons_k = c.slot_cons[k], cons_L = c.slot_cons[L];
+    if (k != L) {
+      c.slot_cons[k] = cons_L;
+      c.cons_slot[cons_L] = k;
+    }
+    c.cons_slot[cons_k] = -1;
+    c.ns = L;
+  }
+  __syncthreads();
+  tsym_rank1(c, T, v_s2, v_s3, L);
 }
 
 // Remove up to four dual slots at once (ks[0 .. kcnt), all >= ne, distinct): block form of the Schur complement,
@@ -2165,18 +2224,19 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
 #else
       const int cnt = 1;
 #endif
-      const int s0 = c.ns;
-      __syncthreads();
-      if (threadIdx.x < cnt) {
-        const int cons = c.list1[k + threadIdx.x];
-        c.slot_cons[s0 + threadIdx.x] = cons;
-        c.cons_slot[cons] = s0 + threadIdx.x;
-      }
-      __syncthreads();
-      if (cnt == 1)
-        insert_slot(c, sc.mu_in, sc.mu_eq);
-      else
+      if (cnt == 1) { // (registers the slot itself: no barrier of its own for the maps)
+        insert_slot(c, sc.mu_in, sc.mu_eq, c.list1[k]);
+      } else {
+        const int s0 = c.ns;
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+          const int cons = c.list1[k + threadIdx.x];
+          c.slot_cons[s0 + threadIdx.x] = cons;
+          c.cons_slot[cons] = s0 + threadIdx.x;
+        }
+        __syncthreads();
         insert_block(c, cnt, sc.mu_in, sc.mu_eq);
+      }
       if (c.overflow) break;
       k += cnt;
     }
