@@ -387,7 +387,9 @@ fill_layout_big(const PqpDims& d, PqpLayout& L, int64_t budget_bytes, int ctas)
   sz[PA_AS] = rnd((int64_t)n * ldb + 4);                 // Bt
   // packed S^-1 (and P during its inversion); sized for the fallback's K^-1 of order n + capacity (pqp_fast_body.inl, kkt_factor)
   const int64_t ordk = (int64_t)n + cap;
-  sz[PA_MS] = rnd(std::max<int64_t>((int64_t)ord * (ord + 1) / 2, ordk * (ordk + 1) / 2) + 4);
+  // (rows padded to an even length, pqp_fast_body.inl ts_idx: order m takes ((m + 1) / 2) (m + 2 - m % 2) doubles)
+  auto packed = [](int64_t mm) { return ((mm + 1) / 2) * (mm + 2 - (mm & 1)); };
+  sz[PA_MS] = rnd(std::max<int64_t>(packed(ord), packed(ordk)) + 4);
   sz[PA_G] = rnd((int64_t)m * ldb + 4);                  // G, full square (lower block triangle used)
   // W; later the fallback's panels (8), right-hand side, solution and NW partial vectors of length n + capacity
   sz[PA_Y] = rnd(std::max<int64_t>((int64_t)n * ldb, (int64_t)(8 + 2 + PQP_NW) * ((ordk + 2) & ~int64_t(1))) + 4);

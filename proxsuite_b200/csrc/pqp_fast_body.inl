@@ -1007,9 +1007,13 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
 // columns 0..i) in the per-CTA global workspace (L2 / HBM), any order. Same interface as the tile storage above;
 // the primitives are loop based (no compile-time block count) and keep several independent loads in flight.
 // ---------------------------------------------------------------------------
+// Row i (columns 0..i) starts at an EVEN offset: rows are padded to an even length, so that a lane can move column
+// PAIRS with 16-byte loads / stores (twice the bytes in flight per instruction: the passes over the triangle are bound
+// by what is in flight). start(i) = i (i + 2) / 2 for even i, (i + 1)^2 / 2 for odd i. The padding
+// element of an even row (column i + 1) is never read as data.
 __device__ __forceinline__ int ts_idx(int, int i, int j)
 {
-  return ((i * (i + 1)) >> 1) + j; // j <= i
+  return ((i + 1) >> 1) * (i + 2 - (i & 1)) + j; // j <= i
 }
 __device__ __forceinline__ double ts_get(const double* T, int, int i, int j)
 {
@@ -1022,7 +1026,7 @@ __device__ __forceinline__ void ts_put(double* T, int, int i, int j, double v)
 }
 __device__ __forceinline__ int ts_extent(int, int n)
 {
-  return (n * (n + 1)) >> 1;
+  return ((n + 1) >> 1) * (n + 2 - (n & 1)); // = ts_idx(n, 0)
 }
 
 // y = T x (order n), x and y must not alias. Uses c.scratch (NW x n doubles).
@@ -1030,39 +1034,46 @@ __device__ __forceinline__ int ts_extent(int, int n)
 //       + sum_{i' > i} T[i'][i] x_i' (column part, AXPY form: lane-stationary accumulators for a group of 256 columns)
 // Row i belongs to the same lane-0 thread in every column group (256 is a multiple of NW): fixed summation order.
 // want_dot: as in the tile version (x . y comes out of the final phase, no trailing barrier).
+// A lane owns four column PAIRS of the group (16-byte loads), two rows of the warp are in flight.
 __device__ __noinline__ double tsym_mv(const Ctx& c, const double* __restrict__ T, const double* __restrict__ x, double* __restrict__ y, int n, bool want_dot = false)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* const scr = c.scratch;
   _Pragma("unroll 1") for (int g0 = 0; g0 < n; g0 += 256) {
-    double acc[8], xl[8];
+    double2 acc[4], xl[4];
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      const int j = g0 + lane + 32 * cc;
-      acc[cc] = 0.0;
-      xl[cc] = (j < n) ? x[j] : 0.0;
+    for (int cc = 0; cc < 4; ++cc) {
+      const int j = g0 + 2 * (lane + 32 * cc);
+      acc[cc] = make_double2(0.0, 0.0);
+      xl[cc] = make_double2((j < n) ? x[j] : 0.0, (j + 1 < n) ? x[j + 1] : 0.0);
     }
     _Pragma("unroll 1") for (int i = g0 + warp; i < n; i += 2 * NW) { // two rows of the warp in flight
       const int i2 = i + NW;
       const bool r2 = i2 < n;
-      const double* row = T + ts_idx(0, i, 0);
-      const double* row2 = T + ts_idx(0, r2 ? i2 : i, 0);
+      const double2* row = reinterpret_cast<const double2*>(T + ts_idx(0, i, 0)) + (g0 >> 1);
+      const double2* row2 = reinterpret_cast<const double2*>(T + ts_idx(0, r2 ? i2 : i, 0)) + (g0 >> 1);
       const double xi = x[i], xi2 = r2 ? x[i2] : 0.0;
-      double a[8], b[8];
+      double2 a[4], b[4];
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        const int j = g0 + lane + 32 * cc;
-        a[cc] = (j <= i) ? row[j] : 0.0;
-        b[cc] = (r2 && j <= i2) ? row2[j] : 0.0;
+      for (int cc = 0; cc < 4; ++cc) {
+        const int j = g0 + 2 * (lane + 32 * cc);
+        a[cc] = (j <= i) ? row[lane + 32 * cc] : make_double2(0.0, 0.0);
+        b[cc] = (r2 && j <= i2) ? row2[lane + 32 * cc] : make_double2(0.0, 0.0);
       }
       double d = 0.0, d2 = 0.0;
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        const int j = g0 + lane + 32 * cc;
-        d = fma(a[cc], xl[cc], d);
-        d2 = fma(b[cc], xl[cc], d2);
-        if (j < i) acc[cc] = fma(a[cc], xi, acc[cc]);
-        if (r2 && j < i2) acc[cc] = fma(b[cc], xi2, acc[cc]);
+      for (int cc = 0; cc < 4; ++cc) {
+        const int j = g0 + 2 * (lane + 32 * cc);
+        if (j + 1 > i) a[cc].y = 0.0;  // padding element of the row (or beyond it)
+        if (j + 1 > i2) b[cc].y = 0.0;
+        d = fma(a[cc].x, xl[cc].x, d);
+        d = fma(a[cc].y, xl[cc].y, d);
+        d2 = fma(b[cc].x, xl[cc].x, d2);
+        d2 = fma(b[cc].y, xl[cc].y, d2);
+        if (j < i) acc[cc].x = fma(a[cc].x, xi, acc[cc].x);
+        if (j + 1 < i) acc[cc].y = fma(a[cc].y, xi, acc[cc].y);
+        if (r2 && j < i2) acc[cc].x = fma(b[cc].x, xi2, acc[cc].x);
+        if (r2 && j + 1 < i2) acc[cc].y = fma(b[cc].y, xi2, acc[cc].y);
       }
       d = warp_sum(d);
       d2 = warp_sum(d2);
@@ -1072,9 +1083,10 @@ __device__ __noinline__ double tsym_mv(const Ctx& c, const double* __restrict__ 
       }
     }
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) {
-      const int j = g0 + lane + 32 * cc;
-      if (j < n) scr[(size_t)warp * n + j] = acc[cc];
+    for (int cc = 0; cc < 4; ++cc) {
+      const int j = g0 + 2 * (lane + 32 * cc);
+      if (j < n) scr[(size_t)warp * n + j] = acc[cc].x;
+      if (j + 1 < n) scr[(size_t)warp * n + j + 1] = acc[cc].y;
     }
   }
   __syncthreads();
@@ -1099,27 +1111,45 @@ __device__ __noinline__ double tsym_mv(const Ctx& c, const double* __restrict__ 
   return 0.0;
 }
 
-// T[i][j] += u_i v_j on the packed lower triangle (j <= i < n). Eight independent read-modify-writes per lane are in
-// flight (the triangle lives in L2 / HBM: with two, a 300 x 300 pass ran at one element per 300 cycles per thread).
+// T[i][j] += u_i v_j on the packed lower triangle (j <= i < n). Two rows of the warp x four column pairs per lane are in
+// flight (128 bytes per thread; the triangle lives in L2 / HBM: with two 8-byte loads in flight a 300 x 300 pass ran
+// at one element per 300 cycles per thread). The loads are forced ahead of the stores with a compiler barrier (ptxas
+// otherwise sinks every load next to its use).
 __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, const double* __restrict__ u, const double* __restrict__ v, int n)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
-    double* row = T + ts_idx(0, i, 0);
-    const double ui = u[i];
-    _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 256) {
-      double a[8], vv[8];
+  _Pragma("unroll 1") for (int i = warp; i < n; i += 2 * NW) {
+    const int i2 = i + NW;
+    const bool r2 = i2 < n;
+    double2* const row = reinterpret_cast<double2*>(T + ts_idx(0, i, 0));
+    double2* const row2 = reinterpret_cast<double2*>(T + ts_idx(0, r2 ? i2 : i, 0));
+    const double ui = u[i], ui2 = r2 ? u[i2] : 0.0;
+    const int last = r2 ? i2 : i; // the longer of the two rows
+    _Pragma("unroll 1") for (int p0 = lane; 2 * p0 <= last; p0 += 128) {
+      double2 a[4], b[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = j0 + 32 * q;
-        a[q] = (j <= i) ? row[j] : 0.0;
-        vv[q] = (j <= i) ? v[j] : 0.0;
+      for (int q = 0; q < 4; ++q) {
+        const int j = 2 * (p0 + 32 * q);
+        a[q] = (j <= i) ? row[p0 + 32 * q] : make_double2(0.0, 0.0);
+        b[q] = (r2 && j <= i2) ? row2[p0 + 32 * q] : make_double2(0.0, 0.0);
       }
-      PQP_LOADS_FIRST(); // keep the eight loads ahead of the stores (ptxas otherwise sinks each load next to its use)
+      PQP_LOADS_FIRST();
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = j0 + 32 * q;
-        if (j <= i) row[j] = fma(ui, vv[q], a[q]);
+      for (int q = 0; q < 4; ++q) {
+        const int j = 2 * (p0 + 32 * q);
+        if (j <= last) {
+          const double v0 = v[j], v1 = (j + 1 <= last) ? v[j + 1] : 0.0;
+          if (j <= i) {
+            a[q].x = fma(ui, v0, a[q].x);
+            if (j + 1 <= i) a[q].y = fma(ui, v1, a[q].y);
+            row[p0 + 32 * q] = a[q];
+          }
+          if (r2) { // (j <= i2 holds)
+            b[q].x = fma(ui2, v0, b[q].x);
+            if (j + 1 <= i2) b[q].y = fma(ui2, v1, b[q].y);
+            row2[p0 + 32 * q] = b[q];
+          }
+        }
       }
     }
   }
@@ -1127,53 +1157,64 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
   __syncthreads();
 }
 
-// T[i][j] += sum_{k<4} U_k[i] V_k[j] (j <= i < n), k = 0..3 in order; U_k = U + k ldv, V_k = V + k ldv (shared memory)
-__device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+// T[i][j] += sum_{k<4} U_k[i] V_k[j] (j <= i < n), k = 0..3 in order; U_k = U + k ldv, V_k = V + k ldv (shared memory;
+// fallback: the global workspace)
+template<bool PANEL_IN_SMEM>
+__device__ __forceinline__ void tsym_rank4_body(double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (c.kkt_mode) { // fallback: the panel vectors are in the global workspace (order n + n_slots does not fit shared memory)
-    _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
-      double* row = T + ts_idx(0, i, 0);
-      const double u0 = U[i], u1 = U[ldv + i], u2 = U[2 * ldv + i], u3 = U[3 * ldv + i];
-      _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 128) {
-        double a[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int j = j0 + 32 * q;
-          a[q] = (j <= i) ? row[j] : 0.0;
-        }
-        PQP_LOADS_FIRST();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int j = j0 + 32 * q;
-          if (j <= i) row[j] = fma(u3, V[3 * ldv + j], fma(u2, V[2 * ldv + j], fma(u1, V[ldv + j], fma(u0, V[j], a[q]))));
-        }
-      }
-    }
-    __syncthreads();
-    return;
+  if (PANEL_IN_SMEM) {
+    PQP_IN_SMEM(U);
+    PQP_IN_SMEM(V);
   }
-  PQP_IN_SMEM(U); // the sweep's panel vectors live in c.scratch: shared memory in every layout of this variant
-  PQP_IN_SMEM(V);
-  _Pragma("unroll 1") for (int i = warp; i < n; i += NW) {
-    double* row = T + ts_idx(0, i, 0);
+  _Pragma("unroll 1") for (int i = warp; i < n; i += 2 * NW) {
+    const int i2 = i + NW;
+    const bool r2 = i2 < n;
+    double2* const row = reinterpret_cast<double2*>(T + ts_idx(0, i, 0));
+    double2* const row2 = reinterpret_cast<double2*>(T + ts_idx(0, r2 ? i2 : i, 0));
     const double u0 = U[i], u1 = U[ldv + i], u2 = U[2 * ldv + i], u3 = U[3 * ldv + i];
-    _Pragma("unroll 1") for (int j0 = lane; j0 <= i; j0 += 256) {
-      double a[8];
+    const int ic = r2 ? i2 : i;
+    const double w0 = r2 ? U[ic] : 0.0, w1 = r2 ? U[ldv + ic] : 0.0, w2 = r2 ? U[2 * ldv + ic] : 0.0, w3 = r2 ? U[3 * ldv + ic] : 0.0;
+    const int last = ic;
+    _Pragma("unroll 1") for (int p0 = lane; 2 * p0 <= last; p0 += 128) {
+      double2 a[4], b[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = j0 + 32 * q;
-        a[q] = (j <= i) ? row[j] : 0.0;
+      for (int q = 0; q < 4; ++q) {
+        const int j = 2 * (p0 + 32 * q);
+        a[q] = (j <= i) ? row[p0 + 32 * q] : make_double2(0.0, 0.0);
+        b[q] = (r2 && j <= i2) ? row2[p0 + 32 * q] : make_double2(0.0, 0.0);
       }
       PQP_LOADS_FIRST();
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = j0 + 32 * q;
-        if (j <= i) row[j] = fma(u3, V[3 * ldv + j], fma(u2, V[2 * ldv + j], fma(u1, V[ldv + j], fma(u0, V[j], a[q]))));
+      for (int q = 0; q < 4; ++q) {
+        const int j = 2 * (p0 + 32 * q);
+        if (j <= last) {
+          const bool two = j + 1 <= last;
+          const double v00 = V[j], v10 = V[ldv + j], v20 = V[2 * ldv + j], v30 = V[3 * ldv + j];
+          const double v01 = two ? V[j + 1] : 0.0, v11 = two ? V[ldv + j + 1] : 0.0, v21 = two ? V[2 * ldv + j + 1] : 0.0, v31 = two ? V[3 * ldv + j + 1] : 0.0;
+          if (j <= i) {
+            a[q].x = fma(u3, v30, fma(u2, v20, fma(u1, v10, fma(u0, v00, a[q].x))));
+            if (j + 1 <= i) a[q].y = fma(u3, v31, fma(u2, v21, fma(u1, v11, fma(u0, v01, a[q].y))));
+            row[p0 + 32 * q] = a[q];
+          }
+          if (r2) {
+            b[q].x = fma(w3, v30, fma(w2, v20, fma(w1, v10, fma(w0, v00, b[q].x))));
+            if (j + 1 <= i2) b[q].y = fma(w3, v31, fma(w2, v21, fma(w1, v11, fma(w0, v01, b[q].y))));
+            row2[p0 + 32 * q] = b[q];
+          }
+        }
       }
     }
   }
-  (void)c;
+}
+__device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+{
+  // the sweep's / block updates' panel vectors live in c.scratch: shared memory in every layout of this variant; the
+  // fallback keeps them in the global workspace (order n + n_slots does not fit shared memory)
+  if (c.kkt_mode)
+    tsym_rank4_body<false>(T, U, V, ldv, n);
+  else
+    tsym_rank4_body<true>(T, U, V, ldv, n);
   __syncthreads();
 }
 

@@ -30,6 +30,11 @@ static inline cudaError_t cudaMalloc(void** p, size_t n)
 {
   n = (n + 255) & ~(size_t)255;
   *p = std::aligned_alloc(256, n ? n : 256);
+  // EMU_POISON=1: device memory starts as signalling garbage (0xFF bytes = NaN doubles, -1 ints) instead of whatever
+  // the allocator returns: a kernel that consumes memory it never wrote (padding of the packed rows, stale workspace)
+  // shows up as NaN results
+  static const bool poison = std::getenv("EMU_POISON") != nullptr;
+  if (*p && poison) std::memset(*p, 0xFF, n ? n : 256);
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 template<class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
