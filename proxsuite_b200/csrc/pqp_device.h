@@ -121,6 +121,7 @@ struct PqpSolveArgs
   int32_t dbg_qp;
   int32_t dbg_cap;
   long long* prof;   // optional per-phase cycle counters (12 entries), NULL = off
+  int32_t prefetch;   // big variant: software L2 prefetch distance of the streaming passes, in warp iterations (0 = off)
   int32_t force_kkt;  // test hook (PQP_FORCE_KKT=1): the big variant solves every QP through the whole-KKT inverse fallback
   unsigned long long watchdog_ns; // 0 = off; per-QP time budget after which the QP is abandoned (status MAX_ITER_REACHED)
   // Fused feed (end-to-end path: init() from host buffers directly followed by solve()):

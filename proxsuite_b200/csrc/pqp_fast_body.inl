@@ -43,6 +43,7 @@ struct Ctx
   int si_valid;    // 0: the dual block has not been formed yet (deferred to the first active-set change)
   int overflow;    // set when an insertion would exceed si_cap (QP is retried by the generic kernel)
   // BIG variant, last-resort fallback: explicit inverse of the WHOLE KKT matrix (see kkt_factor)
+  int pf;          // BIG variant: L2 prefetch distance of the streaming passes (warp iterations ahead, 0 = off)
   int kkt_mode;    // 1: the dual-block path stagnated on this QP; solves go through K^-1 (stored where S^-1 was)
   int kkt_dirty;   // K^-1 must be re-formed before the next solve (active set / mu changed)
   double* kws;     // workspace of the fallback (the W region: free once G is built)
@@ -342,6 +343,20 @@ __device__ void axpy_pass_t(const Ctx& c, const double* __restrict__ base0, int 
 }
 
 #ifdef PQP_BIG
+// Software prefetch into L2 of `count` doubles at p (global memory): lane l of nl cooperating lanes takes every nl-th
+// 128-byte line. The large shapes stream per-CTA workspaces that live in HBM (cfg 5: 27 MB x 296 CTAs); a pass keeps
+// at most 128-256 bytes per thread in flight and stalls a full HBM round trip per batch of rows - with the rows of
+// the iteration after next requested here, the loads find them in L2.
+__device__ __forceinline__ void pf_l2_span(const double* p, int count, int l, int nl)
+{
+#ifndef PQP_CPU_EMU
+  const char* const b = reinterpret_cast<const char*>(p);
+  const int bytes = count * 8;
+  _Pragma("unroll 1") for (int o = l * 128; o < bytes; o += nl * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(__cvta_generic_to_global(b + o)));
+#else
+  (void)p; (void)count; (void)l; (void)nl;
+#endif
+}
 // BIG variant (any number of columns): the same pass, columns handled in groups of 256 (register accumulators for
 // one group at a time), rows predicated instead of peeled. Partial vectors: c.scratch, NW x 2*np doubles.
 __device__ __noinline__ void axpy_pass_big(const Ctx& c, const double* __restrict__ base0, int split, const double* __restrict__ base1, int ld, const int* __restrict__ list, int byid, int nrows, const double* __restrict__ coef, int ncols, double* out, const double* add, double sign, double* raw)
@@ -360,6 +375,18 @@ __device__ __noinline__ void axpy_pass_big(const Ctx& c, const double* __restric
       acc[ch] = make_double2(0.0, 0.0);
     }
     _Pragma("unroll 1") for (int k = warp; k < nrows; k += UNR * NW) {
+      if (c.pf) { // row u = lane / 8 of the batch `pf` iterations ahead, eight lanes per row
+        const int kk = k + c.pf * UNR * NW + (lane >> 3) * NW;
+        if (kk < nrows) {
+          int id = kk;
+          const double* b = base0;
+          if (kk >= split) {
+            b = base1;
+            id = list ? list[kk] : kk - split;
+          }
+          pf_l2_span(b + (size_t)id * (size_t)ld + 2 * g0, min(256, ncols - 2 * g0), lane & 7, 8);
+        }
+      }
       const double2* rp[UNR];
       double cf[UNR];
       bool rv[UNR];
@@ -511,6 +538,10 @@ __device__ __noinline__ void bt_dot_big(const Ctx& c, const double* __restrict__
   const bool two = coef2 != nullptr;
   const bool odd_tail = c.box && (nr & 1); // the last streamed pair then holds the first box column: masked
   _Pragma("unroll 1") for (int jb = warp; jb < n; jb += 4 * NW) {
+    if (c.pf) {
+      const int j = jb + c.pf * 4 * NW + (lane >> 3) * NW;
+      if (j < n) pf_l2_span(c.Bt + (size_t)j * c.ldb, 2 * np, lane & 7, 8);
+    }
     double d1[4] = { 0.0, 0.0, 0.0, 0.0 }, d2[4] = { 0.0, 0.0, 0.0, 0.0 };
     _Pragma("unroll 1") for (int g0 = 0; g0 < np; g0 += 32 * NCH) {
       bool pv[NCH];
@@ -1048,6 +1079,10 @@ __device__ __noinline__ double tsym_mv(const Ctx& c, const double* __restrict__ 
       xl[cc] = make_double2((j < n) ? x[j] : 0.0, (j + 1 < n) ? x[j + 1] : 0.0);
     }
     _Pragma("unroll 1") for (int i = g0 + warp; i < n; i += 2 * NW) { // two rows of the warp in flight
+      if (c.pf) { // the two rows `pf` iterations ahead, sixteen lanes each
+        const int ip = i + c.pf * 2 * NW + (lane >> 4) * NW;
+        if (ip < n) pf_l2_span(T + ts_idx(0, ip, 0) + g0, min(256, ip + 1 - g0), lane & 15, 16);
+      }
       const int i2 = i + NW;
       const bool r2 = i2 < n;
       const double2* row = reinterpret_cast<const double2*>(T + ts_idx(0, i, 0)) + (g0 >> 1);
@@ -1119,6 +1154,10 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   _Pragma("unroll 1") for (int i = warp; i < n; i += 2 * NW) {
+    if (c.pf) {
+      const int ip = i + c.pf * 2 * NW + (lane >> 4) * NW;
+      if (ip < n) pf_l2_span(T + ts_idx(0, ip, 0), ip + 1, lane & 15, 16);
+    }
     const int i2 = i + NW;
     const bool r2 = i2 < n;
     double2* const row = reinterpret_cast<double2*>(T + ts_idx(0, i, 0));
@@ -1160,7 +1199,7 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
 // T[i][j] += sum_{k<4} U_k[i] V_k[j] (j <= i < n), k = 0..3 in order; U_k = U + k ldv, V_k = V + k ldv (shared memory;
 // fallback: the global workspace)
 template<bool PANEL_IN_SMEM>
-__device__ __forceinline__ void tsym_rank4_body(double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+__device__ __forceinline__ void tsym_rank4_body(double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n, int pf)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (PANEL_IN_SMEM) {
@@ -1168,6 +1207,10 @@ __device__ __forceinline__ void tsym_rank4_body(double* __restrict__ T, const do
     PQP_IN_SMEM(V);
   }
   _Pragma("unroll 1") for (int i = warp; i < n; i += 2 * NW) {
+    if (pf) {
+      const int ip = i + pf * 2 * NW + (lane >> 4) * NW;
+      if (ip < n) pf_l2_span(T + ts_idx(0, ip, 0), ip + 1, lane & 15, 16);
+    }
     const int i2 = i + NW;
     const bool r2 = i2 < n;
     double2* const row = reinterpret_cast<double2*>(T + ts_idx(0, i, 0));
@@ -1212,9 +1255,9 @@ __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, co
   // the sweep's / block updates' panel vectors live in c.scratch: shared memory in every layout of this variant; the
   // fallback keeps them in the global workspace (order n + n_slots does not fit shared memory)
   if (c.kkt_mode)
-    tsym_rank4_body<false>(T, U, V, ldv, n);
+    tsym_rank4_body<false>(T, U, V, ldv, n, c.pf);
   else
-    tsym_rank4_body<true>(T, U, V, ldv, n);
+    tsym_rank4_body<true>(T, U, V, ldv, n, c.pf);
   __syncthreads();
 }
 
@@ -3306,6 +3349,9 @@ __device__ __forceinline__ void solve_kernel_body(const PqpSolveArgs& A)
     c.kt2 = c.alphas; // shares the line-search breakpoint array (never live together)
     c.vec_smem = L.in_smem[PA_VEC];
     c.kws = c.W;
+    c.pf = A.prefetch;
+#else
+    c.pf = 0;
 #endif
     c.kkt_mode = 0;
     c.kkt_dirty = 0;
