@@ -840,8 +840,10 @@ enqueue_solve(pqp_batch* b, cudaStream_t st, const PqpLayout& lay, int grid, int
   if (const char* e = std::getenv("PQP_WATCHDOG_MS")) a.watchdog_ns = 1000000ull * (unsigned long long)std::atoll(e);
   if (const char* e = std::getenv("PQP_FORCE_KKT")) a.force_kkt = std::atoi(e);
   // big variant: the per-CTA workspaces of the large shapes (cfg 4: 4.9 MB, cfg 5: 27 MB, times 296 CTAs) live in HBM;
-  // the streaming passes prefetch the rows of the warp iteration after next into L2 (PQP_PREFETCH=0 switches it off)
-  a.prefetch = (lay.kind == 2) ? 2 : 0;
+  // the streaming passes prefetch the rows of the next warp iteration into L2. Measured (profiles/r02_summary.md):
+  // distance 1: cfg 4 +6.7 %, cfg 5 +6 %; 2 and 4: less; cfg 3 (1 MB per CTA, mostly cache resident): -2 % -> off there.
+  // PQP_PREFETCH=<distance> overrides (0 = off).
+  a.prefetch = (lay.kind == 2 && lay.ws_doubles >= 250000) ? 1 : 0;
   if (const char* e = std::getenv("PQP_PREFETCH")) a.prefetch = std::atoi(e);
   a.fused_setup = fused_code;
   a.ready = ready;
