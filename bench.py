@@ -119,13 +119,21 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_HOST_THREADS = None
+
+
 def host_threads():
     """Every host thread this process may use. torchrun exports OMP_NUM_THREADS=1 to its
-    workers; the CPU arm must not inherit that, so the count is passed explicitly."""
-    try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except AttributeError:
-        return max(1, os.cpu_count() or 1)
+    workers; the CPU arm must not inherit that, so the count is passed explicitly. Read ONCE, at the first call (module
+    import): with OMP_PROC_BIND=true libgomp binds the calling thread to one place when it loads, after which
+    sched_getaffinity(0) says 1 - a later call would then make the CPU arm single-threaded on a host without a quota."""
+    global _HOST_THREADS
+    if _HOST_THREADS is None:
+        try:
+            _HOST_THREADS = max(1, len(os.sched_getaffinity(0)))
+        except AttributeError:
+            _HOST_THREADS = max(1, os.cpu_count() or 1)
+    return _HOST_THREADS
 
 
 def cpu_quota():
@@ -159,6 +167,9 @@ def thread_candidates():
     if q:
         c |= {max(1, min(H, int(q + 0.999))), max(1, min(H, 2 * int(q + 0.999)))}
     return sorted(c, reverse=True)
+
+
+host_threads()  # (pinned down before any OpenMP runtime can narrow the affinity mask of this thread)
 
 
 def gpu_numa_cpus(index):
@@ -214,14 +225,17 @@ def make_oracle_batch(sample):
 
 def best_thread_count(batch, candidates):
     """The CPU arm gets the thread count that serves it best on this host: every logical CPU, or
-    half of them (the reference's own default, parallel/qp_solve.hpp:45-49; SMT siblings can hurt).
-    Best of three solves per candidate, after one untimed solve (page-in, thread start, clock ramp)."""
+    half of them (the reference's own default, parallel/qp_solve.hpp:45-49; SMT siblings can hurt), or - under a cgroup
+    quota - the quota. Judged on the SUSTAINED time of four back-to-back solves after one untimed solve, not on the best of
+    them: under a CFS quota an over-subscribed run fits one solve into a fresh 100 ms period now and then (best-of-three said
+    106 ms for 128 threads on a 16-CPU quota) while its steady state is twice that (the timed steps then took 195-199 ms).
+    Ties within 3 % go to the smaller thread count (fewer threads = less quota burnt by spinning / waking)."""
     best_t, best_time, tried = None, None, {}
-    for t in candidates:
+    for t in sorted(candidates):
         batch.solve(t)
-        dt = min(batch.solve(t) for _ in range(3))
+        dt = sum(batch.solve(t) for _ in range(4)) / 4
         tried[t] = dt
-        if best_time is None or dt < best_time:
+        if best_time is None or dt < 0.97 * best_time:
             best_t, best_time = t, dt
     return best_t, tried
 

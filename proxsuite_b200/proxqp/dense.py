@@ -452,12 +452,38 @@ def solve_backward_in_parallel(num_threads=None, qps=None, loss_derivatives=None
         k = e + 1
 
 
-def solve(H=None, g=None, A=None, b=None, C=None, l=None, u=None, x=None, y=None, z=None, eps_abs=None, eps_rel=None,
-          rho=None, mu_eq=None, mu_in=None, verbose=None, compute_preconditioner=True, compute_timings=False,
-          max_iter=None, initial_guess=InitialGuess.EQUALITY_CONSTRAINED_INITIAL_GUESS, check_duality_gap=False,
-          eps_duality_gap_abs=None, eps_duality_gap_rel=None, primal_infeasibility_solving=False,
-          default_H_eigenvalue_estimate=0.0, l_box=None, u_box=None) -> Results:
-    """Free function dense::solve (wrapper.hpp:1000-1233, expose-solve.hpp:20-140)."""
+_SOLVE_TAIL = ("x", "y", "z", "eps_abs", "eps_rel", "rho", "mu_eq", "mu_in", "verbose", "compute_preconditioner", "compute_timings", "max_iter",
+               "initial_guess", "check_duality_gap", "eps_duality_gap_abs", "eps_duality_gap_rel", "primal_infeasibility_solving",
+               "default_H_eigenvalue_estimate")
+_SOLVE_PLAIN = ("H", "g", "A", "b", "C", "l", "u") + _SOLVE_TAIL  # expose-solve.hpp:54-79
+_SOLVE_BOX = ("H", "g", "A", "b", "C", "l", "u", "l_box", "u_box") + _SOLVE_TAIL  # expose-solve.hpp:115-142
+
+
+def solve(*args, **kwargs) -> Results:
+    """Free function dense::solve (wrapper.hpp:1000-1233), both overloads of expose-solve.hpp:20-142 with their positional
+    argument orders: (H, g, A, b, C, l, u, x, y, z, eps_abs, ...) and (H, g, A, b, C, l, u, l_box, u_box, x, y, z, eps_abs, ...).
+    Overload resolution as the reference's binding does it: the plain overload is tried first and is rejected when the
+    argument at its `eps_abs` position (index 10, `y` of the box overload) is an array, or when l_box / u_box are given
+    by keyword."""
+    box_call = "l_box" in kwargs or "u_box" in kwargs or (len(args) > 10 and args[10] is not None and np.ndim(args[10]) >= 1)
+    names = _SOLVE_BOX if box_call else _SOLVE_PLAIN
+    if len(args) > len(names):
+        raise TypeError(f"solve() takes at most {len(names)} positional arguments ({len(args)} given)")
+    kw = dict(zip(names, args))
+    for k, v in kwargs.items():
+        if k not in _SOLVE_BOX:
+            raise TypeError(f"solve() got an unexpected keyword argument '{k}'")
+        if k in kw:
+            raise TypeError(f"solve() got multiple values for argument '{k}'")
+        kw[k] = v
+    return _solve(**kw)
+
+
+def _solve(H=None, g=None, A=None, b=None, C=None, l=None, u=None, x=None, y=None, z=None, eps_abs=None, eps_rel=None,
+           rho=None, mu_eq=None, mu_in=None, verbose=None, compute_preconditioner=True, compute_timings=False,
+           max_iter=None, initial_guess=InitialGuess.EQUALITY_CONSTRAINED_INITIAL_GUESS, check_duality_gap=False,
+           eps_duality_gap_abs=None, eps_duality_gap_rel=None, primal_infeasibility_solving=False,
+           default_H_eigenvalue_estimate=0.0, l_box=None, u_box=None) -> Results:
     n = 0
     if H is not None:
         n = np.asarray(H).shape[0]

@@ -293,6 +293,12 @@ def test_free_solve_function_and_errors(px, oracle):
     r = px.dense.solve(d["H"], d["g"], d["A"], d["b"], d["C"], d["l"], d["u"], eps_abs=EPS, eps_rel=0)
     pri, dua = kkt_residuals(d, r.x, r.y, r.z)
     assert int(r.info.status) == 0 and pri <= EPS and dua <= EPS
+    # the box overload called positionally, in the reference's argument order (expose-solve.hpp:115-126)
+    db = oracle.generate_qp("box_benchmark", 2, 12, 4, 6, sparsity=0.5)
+    rb = px.dense.solve(db["H"], db["g"], db["A"], db["b"], db["C"], db["l"], db["u"], db["l_box"], db["u_box"], None, np.zeros(4), None, EPS, 0)
+    rk = px.dense.solve(db["H"], db["g"], db["A"], db["b"], db["C"], db["l"], db["u"], l_box=db["l_box"], u_box=db["u_box"], eps_abs=EPS, eps_rel=0)
+    assert int(rb.info.status) == 0 and rb.z.shape[0] == 6 + 12 and np.abs(rb.x - rk.x).max() <= 1e-7
+    assert (rb.x >= db["l_box"] - 1e-8).all() and (rb.x <= db["u_box"] + 1e-8).all()
     qp = px.dense.QP(12, 4, 6)
     with pytest.raises(ValueError):  # wrapper.hpp:380-451
         qp.init(d["H"][:5, :5], d["g"], d["A"], d["b"], d["C"], d["l"], d["u"])
