@@ -856,6 +856,122 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
   __syncthreads();
 }
 
+#ifndef PQP_RANK4_DMMA
+#define PQP_RANK4_DMMA 1
+#endif
+#if PQP_RANK4_DMMA
+// T[i][j] += sum_k U[i][k] V[k][j], k = 0..3, on the FP64 tensor cores: a rank-4 update of an 8 x 8 block IS one
+// mma.sync m8n8k4 (A = 8 rows of U, B = 8 columns of V, C = the block; a lane holds C[g][2t], C[g][2t + 1], A[g][t] and
+// B[t][g], g = lane / 4, t = lane % 4). The lower triangle of 16 x 16 blocks (P, Q), Q <= P, is dealt round-robin to the
+// warps; a block is four DMMAs on two A and two B fragments, its C fragments addressed by immediates off one pointer
+// (a 16 x 16 block never straddles a 32 x 32 tile). Against the scalar form (a load, four FMAs and a store per element
+// and lane; 17 % of the kernel's warp instructions, profiles/r02_summary.md section 8) that is ~3 x fewer instructions.
+// Inside a diagonal 32 x 32 tile both halves are stored: only the lower half (i >= j) is computed, and written to (i, j)
+// and (j, i), so the halves stay bit-identical. U is stored row-interleaved (4 doubles per row i), V as four vectors of
+// stride ldv.
+__device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int cap = c.si_cap;
+  PQP_SM(T);
+  PQP_SM(U);
+  PQP_SM(V);
+  const int nP = (n + 15) >> 4;
+  const int total = (nP * (nP + 1)) >> 1;
+  int P = 0, Q = warp; // block of linear index `warp` in the row-major enumeration of the lower block triangle
+  while (Q > P) {
+    Q -= P + 1;
+    ++P;
+  }
+  _Pragma("unroll 1") for (int idx = warp; idx < total; idx += NW) {
+    const int bi = P >> 1, bj = Q >> 1;
+    double* const tile = T + ts_tile(cap, bi, bj);
+    const int rt = 16 * (P & 1) + g, ct = 16 * (Q & 1) + 2 * t; // this lane's row / first column inside the tile (h, w add 8)
+    const int i0 = 16 * P + g;
+    const bool live0 = i0 < n, live1 = i0 + 8 < n;
+    const double a0 = live0 ? U[64 * P + lane] : 0.0;
+    const double a1 = live1 ? U[64 * P + 32 + lane] : 0.0;
+    const int jb = 16 * Q + g;
+    const double b0 = (jb < n) ? V[t * ldv + jb] : 0.0;
+    const double b1 = (jb + 8 < n) ? V[t * ldv + jb + 8] : 0.0;
+    double* const p = tile + rt * TS_LD + ct;
+    double c00[2] = { 0.0, 0.0 }, c01[2] = { 0.0, 0.0 }, c10[2] = { 0.0, 0.0 }, c11[2] = { 0.0, 0.0 };
+    const bool diag = P == Q;
+    if (live0) {
+      c00[0] = p[0];
+      c00[1] = p[1];
+      if (!diag) {
+        c01[0] = p[8];
+        c01[1] = p[9];
+      }
+    }
+    if (live1) {
+      c10[0] = p[8 * TS_LD];
+      c10[1] = p[8 * TS_LD + 1];
+      c11[0] = p[8 * TS_LD + 8];
+      c11[1] = p[8 * TS_LD + 9];
+    }
+    dmma_8x8x4(c00[0], c00[1], a0, b0);
+    if (!diag) dmma_8x8x4(c01[0], c01[1], a0, b1); // (block-uniform: P, Q are)
+    dmma_8x8x4(c10[0], c10[1], a1, b0);
+    dmma_8x8x4(c11[0], c11[1], a1, b1);
+    if (bi != bj) {
+      if (live0) {
+        p[0] = c00[0];
+        p[1] = c00[1];
+        p[8] = c01[0];
+        p[9] = c01[1];
+      }
+      if (live1) {
+        p[8 * TS_LD] = c10[0];
+        p[8 * TS_LD + 1] = c10[1];
+        p[8 * TS_LD + 8] = c11[0];
+        p[8 * TS_LD + 9] = c11[1];
+      }
+    } else {
+      double* const q = tile + ct * TS_LD + rt; // mirror of this lane's first element: (row, col) -> (col, row)
+      const bool lo0 = !diag || g >= 2 * t, lo1 = !diag || g >= 2 * t + 1; // lower half of an 8 x 8 block ON the diagonal
+      if (live0) {
+        if (lo0) {
+          p[0] = c00[0];
+          q[0] = c00[0];
+        }
+        if (lo1) {
+          p[1] = c00[1];
+          q[TS_LD] = c00[1];
+        }
+        if (!diag) {
+          p[8] = c01[0];
+          q[8 * TS_LD] = c01[0];
+          p[9] = c01[1];
+          q[9 * TS_LD] = c01[1];
+        }
+      }
+      if (live1) {
+        p[8 * TS_LD] = c10[0];
+        q[8] = c10[0];
+        p[8 * TS_LD + 1] = c10[1];
+        q[TS_LD + 8] = c10[1];
+        if (lo0) {
+          p[8 * TS_LD + 8] = c11[0];
+          q[8 * TS_LD + 8] = c11[0];
+        }
+        if (lo1) {
+          p[8 * TS_LD + 9] = c11[1];
+          q[9 * TS_LD + 8] = c11[1];
+        }
+      }
+    }
+    Q += NW;
+    while (Q > P) {
+      Q -= P + 1;
+      ++P;
+    }
+  }
+  __syncthreads();
+}
+#else
 // T[i][j] += sum_k U[i][k] V[k][j], k = 0..3 in order. U is stored row-interleaved
 // (4 doubles per row i), V as four vectors of stride ldv. Diagonal tiles: as above.
 __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
@@ -906,7 +1022,247 @@ __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, co
   }
   __syncthreads();
 }
+#endif // PQP_RANK4_DMMA
 
+#ifndef PQP_SWEEP8
+#define PQP_SWEEP8 0
+#endif
+#if PQP_SWEEP8
+// T[i][j] += sum_{k < 8} U[i][k] V[k][j] with V[k][j] = -U[j][k] inv[k] (the rank-8 update of EIGHT consecutive scalar
+// sweeps, see tsym_sweep_invert), on the FP64 tensor cores: per 16 x 16 block of the lower block triangle two chained
+// DMMA m8n8k4 per 8 x 8 sub-block (pivots 0..3, then 4..7: the FMA order of the scalar sweeps), the C fragments loaded
+// and stored once. U0 / U1: pivots 0..3 / 4..7, row-interleaved (4 doubles per row); the B fragments are the A-shaped
+// loads of the column rows scaled by this lane's -inv[4 kc + t] (bit-identical to the V the 4-pivot form stored).
+__device__ __noinline__ void tsym_rank8(const Ctx& c, double* __restrict__ T, const double* __restrict__ U0, const double* __restrict__ U1, const double* __restrict__ inv, int n)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int cap = c.si_cap;
+  PQP_SM(T);
+  PQP_SM(U0);
+  PQP_SM(U1);
+  PQP_SM(inv);
+  const double ni0 = -inv[t], ni1 = -inv[4 + t];
+  const int nP = (n + 15) >> 4;
+  const int total = (nP * (nP + 1)) >> 1;
+  int P = 0, Q = warp; // block of linear index `warp` in the row-major enumeration of the lower block triangle
+  while (Q > P) {
+    Q -= P + 1;
+    ++P;
+  }
+  _Pragma("unroll 1") for (int idx = warp; idx < total; idx += NW) {
+    const int bi = P >> 1, bj = Q >> 1;
+    double* const tile = T + ts_tile(cap, bi, bj);
+    const int rt = 16 * (P & 1) + g, ct = 16 * (Q & 1) + 2 * t; // this lane's row / first column inside the tile (h, w add 8)
+    const int i0 = 16 * P + g, jb = 16 * Q + g;
+    const bool live0 = i0 < n, live1 = i0 + 8 < n;
+    double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0, b00 = 0.0, b01 = 0.0, b10 = 0.0, b11 = 0.0; // [h or w][kc]
+    if (live0) {
+      a00 = U0[64 * P + lane];
+      a01 = U1[64 * P + lane];
+    }
+    if (live1) {
+      a10 = U0[64 * P + 32 + lane];
+      a11 = U1[64 * P + 32 + lane];
+    }
+    if (jb < n) {
+      b00 = U0[64 * Q + lane] * ni0;
+      b01 = U1[64 * Q + lane] * ni1;
+    }
+    if (jb + 8 < n) {
+      b10 = U0[64 * Q + 32 + lane] * ni0;
+      b11 = U1[64 * Q + 32 + lane] * ni1;
+    }
+    double* const p = tile + rt * TS_LD + ct;
+    double c00[2] = { 0.0, 0.0 }, c01[2] = { 0.0, 0.0 }, c10[2] = { 0.0, 0.0 }, c11[2] = { 0.0, 0.0 };
+    const bool diag = P == Q;
+    if (live0) {
+      c00[0] = p[0];
+      c00[1] = p[1];
+      if (!diag) {
+        c01[0] = p[8];
+        c01[1] = p[9];
+      }
+    }
+    if (live1) {
+      c10[0] = p[8 * TS_LD];
+      c10[1] = p[8 * TS_LD + 1];
+      c11[0] = p[8 * TS_LD + 8];
+      c11[1] = p[8 * TS_LD + 9];
+    }
+    dmma_8x8x4(c00[0], c00[1], a00, b00);
+    dmma_8x8x4(c10[0], c10[1], a10, b00);
+    dmma_8x8x4(c11[0], c11[1], a10, b10);
+    if (!diag) dmma_8x8x4(c01[0], c01[1], a00, b10); // (block-uniform: P, Q are)
+    dmma_8x8x4(c00[0], c00[1], a01, b01);
+    dmma_8x8x4(c10[0], c10[1], a11, b01);
+    dmma_8x8x4(c11[0], c11[1], a11, b11);
+    if (!diag) dmma_8x8x4(c01[0], c01[1], a01, b11);
+    if (bi != bj) {
+      if (live0) {
+        p[0] = c00[0];
+        p[1] = c00[1];
+        p[8] = c01[0];
+        p[9] = c01[1];
+      }
+      if (live1) {
+        p[8 * TS_LD] = c10[0];
+        p[8 * TS_LD + 1] = c10[1];
+        p[8 * TS_LD + 8] = c11[0];
+        p[8 * TS_LD + 9] = c11[1];
+      }
+    } else {
+      double* const q = tile + ct * TS_LD + rt; // mirror of this lane's first element: (row, col) -> (col, row)
+      const bool lo0 = !diag || g >= 2 * t, lo1 = !diag || g >= 2 * t + 1; // lower half of an 8 x 8 block ON the diagonal
+      if (live0) {
+        if (lo0) {
+          p[0] = c00[0];
+          q[0] = c00[0];
+        }
+        if (lo1) {
+          p[1] = c00[1];
+          q[TS_LD] = c00[1];
+        }
+        if (!diag) {
+          p[8] = c01[0];
+          q[8 * TS_LD] = c01[0];
+          p[9] = c01[1];
+          q[9 * TS_LD] = c01[1];
+        }
+      }
+      if (live1) {
+        p[8 * TS_LD] = c10[0];
+        q[8] = c10[0];
+        p[8 * TS_LD + 1] = c10[1];
+        q[TS_LD + 8] = c10[1];
+        if (lo0) {
+          p[8 * TS_LD + 8] = c11[0];
+          q[8 * TS_LD + 8] = c11[0];
+        }
+        if (lo1) {
+          p[8 * TS_LD + 9] = c11[1];
+          q[9 * TS_LD + 8] = c11[1];
+        }
+      }
+    }
+    Q += NW;
+    while (Q > P) {
+      Q -= P + 1;
+      ++P;
+    }
+  }
+  __syncthreads();
+}
+
+// In-place inverse of the SPD matrix held in tile storage by BLOCKED symmetric Gauss-Jordan sweeps (Goodnight's sweep
+// operator), EIGHT pivots per pass. One scalar sweep on pivot k maps
+//   T_kk -> -1/d,  T_kj -> T_kj/d,  T_ij -> T_ij - T_ik T_kj / d   (d = T_kk).
+// Eight consecutive sweeps touch an entry outside the pivot rows/columns K only through
+//   T_ij += sum_{k in K} U_ik V_kj,  U_ik = T^(k)_ik (column k just before its own sweep), V_kj = -U_jk / d_k,
+// and U depends only on row i of the n x 8 panel T[:, K] plus the 8 x 8 pivot block. Warp 0 sweeps the pivot block
+// (lane r holds row r, the pivot row is broadcast with shuffles), publishes per pivot 1/d and the scaled pivot row and
+// writes the finished block back; after a barrier every thread sweeps its own panel row in registers, writes it back
+// and stores U (zero on K); one rank-8 pass on the tensor cores applies the rest with the FMA chain the scalar sweeps
+// would have used. Three barriers per eight pivots. After all blocks the array holds -T^-1, negated at the end.
+// Requires n <= NT. `uv`: 8 * ldv doubles. Replaces Ldlt::factorize for the blocks this path inverts
+// (linalg/dense/ldlt.hpp:718-744, factorize.hpp:91-148).
+__device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict__ T, double* __restrict__ uv, int ldv, int n)
+{
+  PQP_SM(T);
+  PQP_SM(uv);
+  const int cap = c.si_cap;
+  double* const U0 = uv;            // [n][4], pivots 0..3 of the pass
+  double* const U1 = uv + 4 * ldv;  // [n][4], pivots 4..7
+  double* const tab = c.red;        // inv[8] | vK[8][8]
+  PQP_SM(tab);
+  const int i = threadIdx.x;
+  for (int k0 = 0; k0 < n; k0 += 8) {
+    const int kb = min(8, n - k0);
+    const int ai = i - k0; // position of this row inside the pivot block when 0 <= ai < kb
+    const bool inK = (ai >= 0) && (ai < kb);
+    // positions of the panel entries (i, k0 .. k0+7): row form (valid when block(k0) <= block(i)),
+    // column form (valid when block(i) <= block(k0)); both inside a diagonal tile
+    const bool rowv = (k0 >> 5) <= (i >> 5), colv = (i >> 5) <= (k0 >> 5);
+    const int rowpos = rowv ? ts_idx(cap, i, k0) : 0;
+    const int colpos = colv ? ts_idx(cap, k0, i) : 0;
+    double p[8] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
+    if (i < n && !inK) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        if (l < kb) p[l] = rowv ? T[rowpos + l] : T[colpos + TS_LD * l];
+      }
+    }
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const int pb = ts_idx(cap, k0, k0);
+      double a[8]; // row `lane` of the (identity padded) pivot block
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a[r] = (lane < kb && r < kb) ? T[pb + TS_LD * lane + r] : ((lane == r) ? 1.0 : 0.0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        double rk[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) rk[r] = __shfl_sync(0xffffffffu, a[r], k);
+        const double inv = 1.0 / rk[k];
+        double vK[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) vK[l] = -rk[l] * inv;
+        if (lane == k) {
+          tab[k] = inv;
+#pragma unroll
+          for (int l = 0; l < 8; ++l) tab[8 + 8 * k + l] = vK[l];
+        }
+        if (lane != k) {
+          const double amk = a[k];
+#pragma unroll
+          for (int l = 0; l < 8; ++l) a[l] = (l == k) ? amk * inv : fma(amk, vK[l], a[l]);
+        } else {
+#pragma unroll
+          for (int l = 0; l < 8; ++l) a[l] = (l == k) ? -inv : a[l] * inv;
+        }
+      }
+      if (lane < kb) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          if (r < kb) T[pb + TS_LD * lane + r] = a[r]; // the finished pivot block (nobody else reads or writes it in this pass)
+        }
+      }
+    }
+    __syncthreads(); // table published; every panel row has been read
+    if (i < n) {
+      double ui[8] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
+      if (!inK) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k < kb) {
+            const double inv = tab[k];
+            const double pk = p[k];
+            ui[k] = pk;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) p[l] = (l == k) ? pk * inv : fma(pk, tab[8 + 8 * k + l], p[l]);
+          }
+        }
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          if (l < kb) {
+            if (rowv) T[rowpos + l] = p[l];
+            if (colv) T[colpos + TS_LD * l] = p[l];
+          }
+        }
+      }
+      reinterpret_cast<double2*>(U0)[2 * i] = make_double2(ui[0], ui[1]);
+      reinterpret_cast<double2*>(U0)[2 * i + 1] = make_double2(ui[2], ui[3]);
+      reinterpret_cast<double2*>(U1)[2 * i] = make_double2(ui[4], ui[5]);
+      reinterpret_cast<double2*>(U1)[2 * i + 1] = make_double2(ui[6], ui[7]);
+    }
+    __syncthreads();
+    tsym_rank8(c, T, U0, U1, tab, n);
+  }
+  const int tot = ts_extent(cap, n);
+  _Pragma("unroll 1") for (int e = threadIdx.x; e < tot; e += NT) T[e] = -T[e];
+  __syncthreads();
+}
+#else // PQP_SWEEP8
 // In-place inverse of the SPD matrix held in tile storage by BLOCKED symmetric
 // Gauss-Jordan sweeps (Goodnight's sweep operator, four pivots per pass).
 // One scalar sweep on pivot k maps
@@ -1025,6 +1381,7 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
   __syncthreads();
 }
 
+#endif // PQP_SWEEP8
 #else // PQP_BIG
 #ifdef PQP_CPU_EMU
 #define PQP_LOADS_FIRST() ((void)0)

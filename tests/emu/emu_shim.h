@@ -143,6 +143,20 @@ __shfl_xor_sync(unsigned, T v, int o)
 }
 template<class T>
 static inline T
+__shfl_sync(unsigned, T v, int src)
+{
+  emu::WarpBuf& w = emu::warp_buf();
+  const int l = emu::lane_id();
+  static_assert(sizeof(T) <= sizeof(double), "shuffle payload");
+  std::memcpy(&w.d[l], &v, sizeof(T));
+  emu::warp_barrier();
+  T r;
+  std::memcpy(&r, &w.d[src & 31], sizeof(T));
+  emu::warp_barrier();
+  return r;
+}
+template<class T>
+static inline T
 __shfl_up_sync(unsigned, T v, int delta)
 {
   emu::WarpBuf& w = emu::warp_buf();
