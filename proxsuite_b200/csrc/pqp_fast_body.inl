@@ -869,10 +869,103 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
 // Inside a diagonal 32 x 32 tile both halves are stored: only the lower half (i >= j) is computed, and written to (i, j)
 // and (j, i), so the halves stay bit-identical. U is stored row-interleaved (4 doubles per row i), V as four vectors of
 // stride ldv.
-__device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+// R1: the rank-1 update T += u v^T (U = u, V = v plain vectors) through the same blocks - the fragments carry u / v in
+// their k = 0 lanes and zeros elsewhere (the three zero products add exactly, so the result is the scalar fma's).
+template<bool R1>
+__device__ __forceinline__ void tsym_rank_dmma_block(double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n, int cap, int P, int Q, int lane)
+{
+  const int g = lane >> 2, t = lane & 3;
+  const int bi = P >> 1, bj = Q >> 1;
+  double* const tile = T + ts_tile(cap, bi, bj);
+  const int rt = 16 * (P & 1) + g, ct = 16 * (Q & 1) + 2 * t; // this lane's row / first column inside the tile (h, w add 8)
+  const int i0 = 16 * P + g;
+  const bool live0 = i0 < n, live1 = i0 + 8 < n;
+  const int jb = 16 * Q + g;
+  double a0, a1, b0, b1;
+  if (R1) {
+    a0 = (live0 && t == 0) ? U[i0] : 0.0;
+    a1 = (live1 && t == 0) ? U[i0 + 8] : 0.0;
+    b0 = (jb < n && t == 0) ? V[jb] : 0.0;
+    b1 = (jb + 8 < n && t == 0) ? V[jb + 8] : 0.0;
+  } else {
+    a0 = live0 ? U[64 * P + lane] : 0.0;
+    a1 = live1 ? U[64 * P + 32 + lane] : 0.0;
+    b0 = (jb < n) ? V[t * ldv + jb] : 0.0;
+    b1 = (jb + 8 < n) ? V[t * ldv + jb + 8] : 0.0;
+  }
+  double* const p = tile + rt * TS_LD + ct;
+  double c00[2] = { 0.0, 0.0 }, c01[2] = { 0.0, 0.0 }, c10[2] = { 0.0, 0.0 }, c11[2] = { 0.0, 0.0 };
+  const bool diag = P == Q;
+  if (live0) {
+    c00[0] = p[0];
+    c00[1] = p[1];
+    if (!diag) {
+      c01[0] = p[8];
+      c01[1] = p[9];
+    }
+  }
+  if (live1) {
+    c10[0] = p[8 * TS_LD];
+    c10[1] = p[8 * TS_LD + 1];
+    c11[0] = p[8 * TS_LD + 8];
+    c11[1] = p[8 * TS_LD + 9];
+  }
+  dmma_8x8x4(c00[0], c00[1], a0, b0);
+  if (!diag) dmma_8x8x4(c01[0], c01[1], a0, b1); // (block-uniform: P, Q are)
+  dmma_8x8x4(c10[0], c10[1], a1, b0);
+  dmma_8x8x4(c11[0], c11[1], a1, b1);
+  if (bi != bj) {
+    if (live0) {
+      p[0] = c00[0];
+      p[1] = c00[1];
+      p[8] = c01[0];
+      p[9] = c01[1];
+    }
+    if (live1) {
+      p[8 * TS_LD] = c10[0];
+      p[8 * TS_LD + 1] = c10[1];
+      p[8 * TS_LD + 8] = c11[0];
+      p[8 * TS_LD + 9] = c11[1];
+    }
+  } else {
+    double* const q = tile + ct * TS_LD + rt; // mirror of this lane's first element: (row, col) -> (col, row)
+    const bool lo0 = !diag || g >= 2 * t, lo1 = !diag || g >= 2 * t + 1; // lower half of an 8 x 8 block ON the diagonal
+    if (live0) {
+      if (lo0) {
+        p[0] = c00[0];
+        q[0] = c00[0];
+      }
+      if (lo1) {
+        p[1] = c00[1];
+        q[TS_LD] = c00[1];
+      }
+      if (!diag) {
+        p[8] = c01[0];
+        q[8 * TS_LD] = c01[0];
+        p[9] = c01[1];
+        q[9 * TS_LD] = c01[1];
+      }
+    }
+    if (live1) {
+      p[8 * TS_LD] = c10[0];
+      q[8] = c10[0];
+      p[8 * TS_LD + 1] = c10[1];
+      q[TS_LD + 8] = c10[1];
+      if (lo0) {
+        p[8 * TS_LD + 8] = c11[0];
+        q[8 * TS_LD + 8] = c11[0];
+      }
+      if (lo1) {
+        p[8 * TS_LD + 9] = c11[1];
+        q[9 * TS_LD + 8] = c11[1];
+      }
+    }
+  }
+}
+template<bool R1>
+__device__ __forceinline__ void tsym_rank_dmma(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
   const int cap = c.si_cap;
   PQP_SM(T);
   PQP_SM(U);
@@ -885,84 +978,7 @@ __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, co
     ++P;
   }
   _Pragma("unroll 1") for (int idx = warp; idx < total; idx += NW) {
-    const int bi = P >> 1, bj = Q >> 1;
-    double* const tile = T + ts_tile(cap, bi, bj);
-    const int rt = 16 * (P & 1) + g, ct = 16 * (Q & 1) + 2 * t; // this lane's row / first column inside the tile (h, w add 8)
-    const int i0 = 16 * P + g;
-    const bool live0 = i0 < n, live1 = i0 + 8 < n;
-    const double a0 = live0 ? U[64 * P + lane] : 0.0;
-    const double a1 = live1 ? U[64 * P + 32 + lane] : 0.0;
-    const int jb = 16 * Q + g;
-    const double b0 = (jb < n) ? V[t * ldv + jb] : 0.0;
-    const double b1 = (jb + 8 < n) ? V[t * ldv + jb + 8] : 0.0;
-    double* const p = tile + rt * TS_LD + ct;
-    double c00[2] = { 0.0, 0.0 }, c01[2] = { 0.0, 0.0 }, c10[2] = { 0.0, 0.0 }, c11[2] = { 0.0, 0.0 };
-    const bool diag = P == Q;
-    if (live0) {
-      c00[0] = p[0];
-      c00[1] = p[1];
-      if (!diag) {
-        c01[0] = p[8];
-        c01[1] = p[9];
-      }
-    }
-    if (live1) {
-      c10[0] = p[8 * TS_LD];
-      c10[1] = p[8 * TS_LD + 1];
-      c11[0] = p[8 * TS_LD + 8];
-      c11[1] = p[8 * TS_LD + 9];
-    }
-    dmma_8x8x4(c00[0], c00[1], a0, b0);
-    if (!diag) dmma_8x8x4(c01[0], c01[1], a0, b1); // (block-uniform: P, Q are)
-    dmma_8x8x4(c10[0], c10[1], a1, b0);
-    dmma_8x8x4(c11[0], c11[1], a1, b1);
-    if (bi != bj) {
-      if (live0) {
-        p[0] = c00[0];
-        p[1] = c00[1];
-        p[8] = c01[0];
-        p[9] = c01[1];
-      }
-      if (live1) {
-        p[8 * TS_LD] = c10[0];
-        p[8 * TS_LD + 1] = c10[1];
-        p[8 * TS_LD + 8] = c11[0];
-        p[8 * TS_LD + 9] = c11[1];
-      }
-    } else {
-      double* const q = tile + ct * TS_LD + rt; // mirror of this lane's first element: (row, col) -> (col, row)
-      const bool lo0 = !diag || g >= 2 * t, lo1 = !diag || g >= 2 * t + 1; // lower half of an 8 x 8 block ON the diagonal
-      if (live0) {
-        if (lo0) {
-          p[0] = c00[0];
-          q[0] = c00[0];
-        }
-        if (lo1) {
-          p[1] = c00[1];
-          q[TS_LD] = c00[1];
-        }
-        if (!diag) {
-          p[8] = c01[0];
-          q[8 * TS_LD] = c01[0];
-          p[9] = c01[1];
-          q[9 * TS_LD] = c01[1];
-        }
-      }
-      if (live1) {
-        p[8 * TS_LD] = c10[0];
-        q[8] = c10[0];
-        p[8 * TS_LD + 1] = c10[1];
-        q[TS_LD + 8] = c10[1];
-        if (lo0) {
-          p[8 * TS_LD + 8] = c11[0];
-          q[8 * TS_LD + 8] = c11[0];
-        }
-        if (lo1) {
-          p[8 * TS_LD + 9] = c11[1];
-          q[9 * TS_LD + 8] = c11[1];
-        }
-      }
-    }
+    tsym_rank_dmma_block<R1>(T, U, V, ldv, n, cap, P, Q, lane);
     Q += NW;
     while (Q > P) {
       Q -= P + 1;
@@ -971,6 +987,19 @@ __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, co
   }
   __syncthreads();
 }
+__device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
+{
+  tsym_rank_dmma<false>(c, T, U, V, ldv, n);
+}
+#ifndef PQP_RANK1_DMMA
+#define PQP_RANK1_DMMA 1
+#endif
+#if PQP_RANK1_DMMA
+__device__ __noinline__ void tsym_rank1_dmma(const Ctx& c, double* __restrict__ T, const double* __restrict__ u, const double* __restrict__ v, int n)
+{
+  tsym_rank_dmma<true>(c, T, u, v, 0, n);
+}
+#endif
 #else
 // T[i][j] += sum_k U[i][k] V[k][j], k = 0..3 in order. U is stored row-interleaved
 // (4 doubles per row i), V as four vectors of stride ldv. Diagonal tiles: as above.
@@ -1263,6 +1292,152 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
   __syncthreads();
 }
 #else // PQP_SWEEP8
+#ifndef PQP_SWEEP_LA
+#define PQP_SWEEP_LA 1
+#endif
+#if PQP_SWEEP_LA && PQP_RANK4_DMMA
+// Sweep of the (identity padded) 4 x 4 pivot block at (k0, k0), redundantly by every lane of ONE warp: publishes per
+// pivot 1/d and the scaled pivot row, plus the finished block (tab: inv[4] | vK[4][4] | block [4][4]).
+__device__ __forceinline__ void sweep_pivot_block(const double* __restrict__ T, double* __restrict__ tab, int cap, int k0, int kb, int lane)
+{
+  const int pb = ts_idx(cap, k0, k0);
+  double a[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a[q][r] = (q < kb && r < kb) ? T[pb + TS_LD * q + r] : ((q == r) ? 1.0 : 0.0);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double inv = 1.0 / a[k][k];
+    double vK[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) vK[l] = -a[k][l] * inv;
+    if (lane == 0) {
+      tab[k] = inv;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) tab[4 + 4 * k + l] = vK[l];
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (m != k) {
+        const double amk = a[m][k];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) a[m][l] = (l == k) ? amk * inv : fma(amk, vK[l], a[m][l]);
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a[k][l] = (l == k) ? -inv : a[k][l] * inv;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) tab[20 + 4 * q + r] = a[q][r];
+    }
+  }
+}
+
+// In-place inverse of the SPD matrix held in tile storage by BLOCKED symmetric Gauss-Jordan sweeps (Goodnight's sweep
+// operator, four pivots per pass), the pivot phase one pass AHEAD. One scalar sweep on pivot k maps
+//   T_kk -> -1/d,  T_kj -> T_kj/d,  T_ij -> T_ij - T_ik T_kj / d   (d = T_kk).
+// Four consecutive sweeps touch an entry outside the pivot rows/columns K only through
+//   T_ij += sum_{k in K} U_ik V_kj,  U_ik = T^(k)_ik (column k just before its own sweep), V_kj = -U_jk / d_k,
+// and U depends only on row i of the n x 4 panel T[:, K] plus the 4 x 4 pivot block. Per pass: every thread sweeps its
+// own panel row in registers with the published pivot table, writes the finished K rows / columns back and stores U, V
+// (zero on K); after a barrier the rank-4 pass (tensor cores, tsym_rank_dmma_block) applies the rest - and the warp
+// that owns the 16 x 16 block holding the NEXT pivot block updates that block first, sweeps the 4 x 4 pivot block (the
+// only sequential chain: four dependent reciprocals) and publishes the next table while the other warps are still
+// updating: the chain is off the critical path and a pass has two barriers instead of three. Same arithmetic, element
+// by element, as the three-barrier form (kept below). After all blocks the array holds -T^-1, negated at the end.
+// Requires n <= NT. `uv`: 8 * ldv doubles. Replaces Ldlt::factorize for the blocks this path inverts
+// (linalg/dense/ldlt.hpp:718-744, factorize.hpp:91-148).
+__device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict__ T, double* __restrict__ uv, int ldv, int n)
+{
+  PQP_SM(T);
+  PQP_SM(uv);
+  const int cap = c.si_cap;
+  double* const U = uv;            // [n][4]
+  double* const V = uv + 4 * ldv;  // [4][ldv]
+  double* const tab = c.red;       // inv[4] | vK[4][4] | final pivot block [4][4]
+  PQP_SM(tab);
+  const int i = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nP = (n + 15) >> 4;
+  const int total = (nP * (nP + 1)) >> 1;
+  if (warp == 0) sweep_pivot_block(T, tab, cap, 0, min(4, n), lane);
+  __syncthreads();
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    const int kb = min(4, n - k0);
+    const int ai = i - k0; // position of this row inside the pivot block when 0 <= ai < kb
+    const bool inK = (ai >= 0) && (ai < kb);
+    // positions of the panel entries (i, k0 .. k0+3): row form (valid when block(k0) <= block(i)),
+    // column form (valid when block(i) <= block(k0)); both inside a diagonal tile
+    const bool rowv = (k0 >> 5) <= (i >> 5), colv = (i >> 5) <= (k0 >> 5);
+    const int rowpos = rowv ? ts_idx(cap, i, k0) : 0;
+    const int colpos = colv ? ts_idx(cap, k0, i) : 0;
+    if (i < n) {
+      double p[4] = { 0.0, 0.0, 0.0, 0.0 };
+      double ui[4] = { 0.0, 0.0, 0.0, 0.0 }, vi[4] = { 0.0, 0.0, 0.0, 0.0 };
+      if (!inK) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          if (l < kb) p[l] = rowv ? T[rowpos + l] : T[colpos + TS_LD * l];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < kb) {
+            const double inv = tab[k];
+            const double pk = p[k];
+            ui[k] = pk;
+            vi[k] = -pk * inv;
+#pragma unroll
+            for (int l = 0; l < 4; ++l) p[l] = (l == k) ? pk * inv : fma(pk, tab[4 + 4 * k + l], p[l]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) p[l] = tab[20 + 4 * ai + l]; // finished pivot row
+      }
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        if (l < kb) {
+          if (rowv) T[rowpos + l] = p[l];
+          if (colv && !inK) T[colpos + TS_LD * l] = p[l];
+        }
+        V[l * ldv + i] = vi[l];
+      }
+      reinterpret_cast<double2*>(U)[2 * i] = make_double2(ui[0], ui[1]);
+      reinterpret_cast<double2*>(U)[2 * i + 1] = make_double2(ui[2], ui[3]);
+    }
+    __syncthreads(); // panel, U, V complete; every reader of the table is past it
+    // rank-4 pass; the block holding the next pivot block first, by its owner, which then sweeps that pivot block
+    const int kn = k0 + 4;
+    const int Pn = kn >> 4, idxn = (kn < n) ? ((Pn * (Pn + 1)) >> 1) + Pn : -1;
+    if (idxn >= 0 && (idxn & (NW - 1)) == warp) {
+      tsym_rank_dmma_block<false>(T, U, V, ldv, n, cap, Pn, Pn, lane);
+      __syncwarp();
+      sweep_pivot_block(T, tab, cap, kn, min(4, n - kn), lane);
+    }
+    int P = 0, Q = warp;
+    while (Q > P) {
+      Q -= P + 1;
+      ++P;
+    }
+    _Pragma("unroll 1") for (int idx = warp; idx < total; idx += NW) {
+      if (idx != idxn) tsym_rank_dmma_block<false>(T, U, V, ldv, n, cap, P, Q, lane);
+      Q += NW;
+      while (Q > P) {
+        Q -= P + 1;
+        ++P;
+      }
+    }
+    __syncthreads();
+  }
+  const int tot = ts_extent(cap, n);
+  _Pragma("unroll 1") for (int e = threadIdx.x; e < tot; e += NT) T[e] = -T[e];
+  __syncthreads();
+}
+#else // PQP_SWEEP_LA
 // In-place inverse of the SPD matrix held in tile storage by BLOCKED symmetric
 // Gauss-Jordan sweeps (Goodnight's sweep operator, four pivots per pass).
 // One scalar sweep on pivot k maps
@@ -1381,6 +1556,7 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
   __syncthreads();
 }
 
+#endif // PQP_SWEEP_LA
 #endif // PQP_SWEEP8
 #else // PQP_BIG
 #ifdef PQP_CPU_EMU
@@ -1718,6 +1894,15 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
   __syncthreads();
 }
 #endif // PQP_BIG
+#undef PQP_TSYM_RANK1
+#if !defined(PQP_BIG) && PQP_RANK1_DMMA
+#define PQP_TSYM_RANK1 tsym_rank1_dmma // (tile storage: the rank-1 updates of insertion / deletion on the tensor-core blocks)
+#else
+#define PQP_TSYM_RANK1 tsym_rank1
+#endif
+#ifndef PQP_TILE_BLOCK
+#define PQP_TILE_BLOCK 0 // tile kernel: block (rank-4) insertion / deletion as in the big variant (A/B switch)
+#endif
 
 __device__ __forceinline__ int row_id(const Ctx& c, int s)
 {
@@ -1965,7 +2150,7 @@ __device__ __noinline__ void insert_slot(Ctx& c, double mu, double mu_eq, int co
     c.ns = s + 1;
   }
   __syncthreads(); // w, w / delta complete; also the barrier c.red needed after the fused reduction
-  if (s > 0) tsym_rank1(c, c.Si, v_s1, v_s2, s);
+  if (s > 0) PQP_TSYM_RANK1(c, c.Si, v_s1, v_s2, s);
 }
 
 // Remove dual slot k (k >= ne): Schur complement of the explicit inverse,
@@ -2192,7 +2377,7 @@ __device__ __noinline__ void delete_slot(Ctx& c, int k)
     c.ns = L;
   }
   __syncthreads();
-  tsym_rank1(c, T, v_s2, v_s3, L);
+  PQP_TSYM_RANK1(c, T, v_s2, v_s3, L);
 }
 
 // Remove up to four dual slots at once (ks[0 .. kcnt), all >= ne, distinct): block form of the Schur complement,
@@ -2620,7 +2805,7 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
   });
   long long tp = PROF_T0();
   for (int k = ndel - 1; k >= 0;) { // from the last slot to the first, four at a time
-#ifdef PQP_BIG
+#if defined(PQP_BIG) || PQP_TILE_BLOCK
     const int cnt = min(4, k + 1);
 #else
     const int cnt = 1; // shared-memory S^-1 (tile kernel): a pass is cheap, the block form only adds code (measured: -6 % at cfg 2)
@@ -2660,7 +2845,7 @@ __device__ __noinline__ void active_set_change(Ctx& c, Scal& sc)
     }
   } else {
     for (int k = 0; k < nadd;) { // four at a time where S^-1 is streamed from L2 / HBM (big variant)
-#ifdef PQP_BIG
+#if defined(PQP_BIG) || PQP_TILE_BLOCK
       const int cnt = min(4, nadd - k);
 #else
       const int cnt = 1;
