@@ -1783,14 +1783,114 @@ __device__ __forceinline__ void tsym_rank4_body(double* __restrict__ T, const do
     }
   }
 }
+#ifndef PQP_BIG_RANK4_DMMA
+#define PQP_BIG_RANK4_DMMA 1
+#endif
+#ifndef PQP_BIG_DMMA_MAX_N
+#define PQP_BIG_DMMA_MAX_N 288
+#endif
+// The same update on the FP64 tensor cores (packed storage): the lower triangle in blocks of 16 rows x 32 columns, dealt
+// round-robin to the warps; an 8 x 8 sub-block is one mma.sync m8n8k4 (A = 8 rows of U^T, B = 8 columns of V; a lane
+// holds C[g][2t], C[g][2t + 1] = one 16-byte pair of the packed row, g = lane / 4, t = lane % 4). Eight pairs per lane
+// are in flight per block (128 bytes, as in the scalar form); sub-blocks above the diagonal are skipped, elements above
+// it masked (a pair starting ON the diagonal of an even row carries the row's padding element, never read as data).
+// Roughly half the instructions of the scalar form (four FMAs per element and lane).
+template<bool PANEL_IN_SMEM>
+__device__ __forceinline__ void tsym_rank4_dmma_body(double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n, int pf)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  if (PANEL_IN_SMEM) {
+    PQP_IN_SMEM(U);
+    PQP_IN_SMEM(V);
+  }
+  const int nR = (n + 15) >> 4;
+  int R = 0, Cb = warp; // row block R (16 rows) has the column blocks 0 .. R / 2 (32 columns each)
+  while (R < nR && Cb > (R >> 1)) {
+    Cb -= (R >> 1) + 1;
+    ++R;
+  }
+  int Rp = R, Cp = Cb + pf * NW; // cursor of the software prefetch, `pf` turns ahead
+  while (Rp < nR && Cp > (Rp >> 1)) {
+    Cp -= (Rp >> 1) + 1;
+    ++Rp;
+  }
+  _Pragma("unroll 1") while (R < nR) {
+    const int i0 = 16 * R + g, jc = 32 * Cb;
+    const bool live0 = i0 < n, live1 = i0 + 8 < n;
+    if (pf) { // the block this warp takes `pf` turns ahead: one 128-byte line per lane (16 rows x 2 lines)
+      const int ip = 16 * Rp + (lane & 15), jp = 32 * Cp + 16 * (lane >> 4);
+      if (Rp < nR && ip < n && jp <= ip) pf_l2_span(T + ts_idx(0, ip, 0) + jp, 1, 0, 1);
+      Cp += NW;
+      while (Rp < nR && Cp > (Rp >> 1)) {
+        Cp -= (Rp >> 1) + 1;
+        ++Rp;
+      }
+    }
+    double a[2], b[4];
+    a[0] = live0 ? U[t * ldv + i0] : 0.0;
+    a[1] = live1 ? U[t * ldv + i0 + 8] : 0.0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int j = jc + 8 * w + g;
+      b[w] = (j < n) ? V[t * ldv + j] : 0.0;
+    }
+    double* const r0 = T + ts_idx(0, live0 ? i0 : 0, 0);
+    double* const r1 = T + ts_idx(0, live1 ? i0 + 8 : 0, 0);
+    double2 cc[2][4];
+    bool ex[2][4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int j = jc + 8 * w + 2 * t;
+      ex[0][w] = live0 && j <= i0;
+      ex[1][w] = live1 && j <= i0 + 8;
+      cc[0][w] = ex[0][w] ? *reinterpret_cast<const double2*>(r0 + j) : make_double2(0.0, 0.0);
+      cc[1][w] = ex[1][w] ? *reinterpret_cast<const double2*>(r1 + j) : make_double2(0.0, 0.0);
+    }
+    PQP_LOADS_FIRST();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        if (jc + 8 * w <= 16 * R + 8 * h + 7) dmma_8x8x4(cc[h][w].x, cc[h][w].y, a[h], b[w]); // (warp-uniform: sub-block not above the diagonal)
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int j = jc + 8 * w + 2 * t;
+      if (ex[0][w]) *reinterpret_cast<double2*>(r0 + j) = cc[0][w];
+      if (ex[1][w]) *reinterpret_cast<double2*>(r1 + j) = cc[1][w];
+    }
+    Cb += NW;
+    while (R < nR && Cb > (R >> 1)) {
+      Cb -= (R >> 1) + 1;
+      ++R;
+    }
+  }
+}
 __device__ __noinline__ void tsym_rank4(const Ctx& c, double* __restrict__ T, const double* __restrict__ U, const double* __restrict__ V, int ldv, int n)
 {
   // the sweep's / block updates' panel vectors live in c.scratch: shared memory in every layout of this variant; the
   // fallback keeps them in the global workspace (order n + n_slots does not fit shared memory)
-  if (c.kkt_mode)
-    tsym_rank4_body<false>(T, U, V, ldv, n, c.pf);
-  else
-    tsym_rank4_body<true>(T, U, V, ldv, n, c.pf);
+  // tensor-core blocks up to order PQP_BIG_DMMA_MAX_N, whole-row streaming above (same-box A/B, profiles/r02_ab_big_rank4_dmma.log:
+  // cfg 3 (orders ~100-130, L1 resident) +12.5 %, cfg 4 (orders 230-256, L2) +1.8 %, cfg 5 (orders 350-450, HBM) -2.7 %: there
+  // the 256-byte row segments of a block lose to rows streamed end to end)
+#if PQP_BIG_RANK4_DMMA
+  const bool dmma = n <= PQP_BIG_DMMA_MAX_N; // block-uniform
+#else
+  const bool dmma = false;
+#endif
+  if (c.kkt_mode) {
+    if (dmma)
+      tsym_rank4_dmma_body<false>(T, U, V, ldv, n, c.pf);
+    else
+      tsym_rank4_body<false>(T, U, V, ldv, n, c.pf);
+  } else {
+    if (dmma)
+      tsym_rank4_dmma_body<true>(T, U, V, ldv, n, c.pf);
+    else
+      tsym_rank4_body<true>(T, U, V, ldv, n, c.pf);
+  }
   __syncthreads();
 }
 
