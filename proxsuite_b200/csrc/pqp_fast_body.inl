@@ -97,6 +97,9 @@ struct Ctx
   double* const v_red = c.red; PQP_SM(v_red); (void)v_red;   \
   (void)0
 
+#ifndef PQP_REDUX_MAX
+#define PQP_REDUX_MAX 1
+#endif
 __device__ __forceinline__ double nanmax(double a, double b)
 {
   return (b > a || b != b) ? b : a;
@@ -107,11 +110,23 @@ __device__ __forceinline__ double warp_sum(double v)
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+// NaN-propagating maximum over the warp of values with the sign bit CLEAR (every caller reduces |.| values or 0 / 1
+// flags): for such doubles the order of the bit patterns is the order of the values, with every NaN above +inf, so the
+// maximum is the 64-bit unsigned maximum of the patterns - two redux.sync.max.u32 (high words, then the low words of the
+// lanes that hold the winning high word) instead of a five-step shuffle butterfly with two compares and two selects
+// per step. Returns the same value as the butterfly of nanmax() (a NaN if any lane holds one, else the largest).
 __device__ __forceinline__ double warp_max(double v)
 {
+#if PQP_REDUX_MAX
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned hmax = __reduce_max_sync(FULL, hi);
+  const unsigned lmax = __reduce_max_sync(FULL, (hi == hmax) ? lo : 0u);
+  return __hiloint2double((int)hmax, (int)lmax);
+#else
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = nanmax(v, __shfl_xor_sync(FULL, v, o));
   return v;
+#endif
 }
 
 // K sums followed by KM maxima reduced over the CTA; the result is returned to
@@ -141,10 +156,14 @@ __device__ void block_reduce(const Ctx& c, double* sums, double* maxs)
   }
 #pragma unroll
   for (int k = 0; k < KM; ++k) {
+#if PQP_REDUX_MAX
+    maxs[k] = warp_max(v_red[(lane & (NW - 1)) * (KS + KM) + KS + k]); // (every warp value four times over the lanes)
+#else
     double m = v_red[KS + k];
 #pragma unroll
     for (int w = 1; w < NW; ++w) m = nanmax(m, v_red[w * (KS + KM) + KS + k]);
     maxs[k] = m;
+#endif
   }
   __syncthreads();
 }

@@ -141,6 +141,44 @@ __shfl_xor_sync(unsigned, T v, int o)
   emu::warp_barrier();
   return r;
 }
+static inline unsigned
+__reduce_max_sync(unsigned, unsigned v)
+{
+  emu::WarpBuf& w = emu::warp_buf();
+  const int l = emu::lane_id();
+  std::memcpy(&w.d[l], &v, sizeof(v));
+  emu::warp_barrier();
+  unsigned m = 0;
+  for (int k = 0; k < 32; ++k) {
+    unsigned x;
+    std::memcpy(&x, &w.d[k], sizeof(x));
+    m = x > m ? x : m;
+  }
+  emu::warp_barrier();
+  return m;
+}
+static inline int
+__double2hiint(double v)
+{
+  unsigned long long b;
+  std::memcpy(&b, &v, 8);
+  return (int)(unsigned)(b >> 32);
+}
+static inline int
+__double2loint(double v)
+{
+  unsigned long long b;
+  std::memcpy(&b, &v, 8);
+  return (int)(unsigned)(b & 0xffffffffull);
+}
+static inline double
+__hiloint2double(int hi, int lo)
+{
+  const unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned long long)(unsigned)lo;
+  double v;
+  std::memcpy(&v, &b, 8);
+  return v;
+}
 template<class T>
 static inline T
 __shfl_sync(unsigned, T v, int src)
