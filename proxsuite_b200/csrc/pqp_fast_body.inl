@@ -878,6 +878,9 @@ __device__ __noinline__ void tsym_rank1(const Ctx& c, double* __restrict__ T, co
 #ifndef PQP_RANK4_DMMA
 #define PQP_RANK4_DMMA 1
 #endif
+#ifndef PQP_DMMA_FAST_PATH
+#define PQP_DMMA_FAST_PATH 0 // (measured: -1.3 % at cfg 2, profiles/r02_ab_fast_path.log)
+#endif
 #if PQP_RANK4_DMMA
 // T[i][j] += sum_k U[i][k] V[k][j], k = 0..3, on the FP64 tensor cores: a rank-4 update of an 8 x 8 block IS one
 // mma.sync m8n8k4 (A = 8 rows of U, B = 8 columns of V, C = the block; a lane holds C[g][2t], C[g][2t + 1], A[g][t] and
@@ -898,6 +901,38 @@ __device__ __forceinline__ void tsym_rank_dmma_block(double* __restrict__ T, con
   double* const tile = T + ts_tile(cap, bi, bj);
   const int rt = 16 * (P & 1) + g, ct = 16 * (Q & 1) + 2 * t; // this lane's row / first column inside the tile (h, w add 8)
   const int i0 = 16 * P + g;
+#if PQP_DMMA_FAST_PATH
+  if (bi != bj && 16 * P + 15 < n) { // a block of an off-diagonal tile with all sixteen rows live: no predicates, no mirror
+    double a0, a1, b0, b1;
+    if (R1) {
+      a0 = (t == 0) ? U[i0] : 0.0;
+      a1 = (t == 0) ? U[i0 + 8] : 0.0;
+      b0 = (t == 0) ? V[16 * Q + g] : 0.0;
+      b1 = (t == 0) ? V[16 * Q + g + 8] : 0.0;
+    } else {
+      a0 = U[64 * P + lane];
+      a1 = U[64 * P + 32 + lane];
+      b0 = V[t * ldv + 16 * Q + g];
+      b1 = V[t * ldv + 16 * Q + g + 8];
+    }
+    double* const p = tile + rt * TS_LD + ct;
+    double c00x = p[0], c00y = p[1], c01x = p[8], c01y = p[9];
+    double c10x = p[8 * TS_LD], c10y = p[8 * TS_LD + 1], c11x = p[8 * TS_LD + 8], c11y = p[8 * TS_LD + 9];
+    dmma_8x8x4(c00x, c00y, a0, b0);
+    dmma_8x8x4(c01x, c01y, a0, b1);
+    dmma_8x8x4(c10x, c10y, a1, b0);
+    dmma_8x8x4(c11x, c11y, a1, b1);
+    p[0] = c00x;
+    p[1] = c00y;
+    p[8] = c01x;
+    p[9] = c01y;
+    p[8 * TS_LD] = c10x;
+    p[8 * TS_LD + 1] = c10y;
+    p[8 * TS_LD + 8] = c11x;
+    p[8 * TS_LD + 9] = c11y;
+    return;
+  }
+#endif
   const bool live0 = i0 < n, live1 = i0 + 8 < n;
   const int jb = 16 * Q + g;
   double a0, a1, b0, b1;
@@ -933,6 +968,10 @@ __device__ __forceinline__ void tsym_rank_dmma_block(double* __restrict__ T, con
   if (!diag) dmma_8x8x4(c01[0], c01[1], a0, b1); // (block-uniform: P, Q are)
   dmma_8x8x4(c10[0], c10[1], a1, b0);
   dmma_8x8x4(c11[0], c11[1], a1, b1);
+  // In a diagonal 8 x 8 sub-block every lane has read its C pair above, upper-half lanes included, and the mirror stores
+  // below write those upper-half elements from other lanes. The reads feed the (warp-converged) mma.sync, so they are
+  // complete before any store issues; the barrier states that order for the memory model and for racecheck.
+  __syncwarp();
   if (bi != bj) {
     if (live0) {
       p[0] = c00[0];
@@ -1146,6 +1185,7 @@ __device__ __noinline__ void tsym_rank8(const Ctx& c, double* __restrict__ T, co
     dmma_8x8x4(c10[0], c10[1], a11, b01);
     dmma_8x8x4(c11[0], c11[1], a11, b11);
     if (!diag) dmma_8x8x4(c01[0], c01[1], a01, b11);
+    __syncwarp(); // (reads of the upper-half elements of a diagonal sub-block before the mirror stores, see tsym_rank_dmma_block)
     if (bi != bj) {
       if (live0) {
         p[0] = c00[0];
