@@ -2059,6 +2059,9 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
 #else
 #define PQP_TSYM_RANK1 tsym_rank1
 #endif
+#ifndef PQP_BTLAM_AXPY
+#define PQP_BTLAM_AXPY 0 // tile kernel: B^T lam of solve_kkt as an AXPY pass over the active rows of A_s / C_s (A/B switch)
+#endif
 #ifndef PQP_TILE_BLOCK
 #define PQP_TILE_BLOCK 0 // tile kernel: block (rank-4) insertion / deletion as in the big variant (A/B switch)
 #endif
@@ -2220,6 +2223,16 @@ __device__ __noinline__ void solve_kkt(Ctx& c, const double* b1, const double* b
   _Pragma("unroll 1") for (int s = threadIdx.x; s < ns; s += NT) v_s1[s] = c.kt[row_id(c, s)] - b2[s];
   __syncthreads();
   tsym_mv(c, c.Si, v_s1, os, ns);
+#if !defined(PQP_BIG) && PQP_BTLAM_AXPY
+  // t2 = b1 - B^T lam in AXPY form over the ACTIVE rows only: the n_eq rows of A_s, then row slot_cons[s] of C_s for every
+  // inequality slot s, weighted by lam[s] (one pass over ~n_s rows of n doubles instead of the dot form over all n rows of
+  // Bt, n_eq + n_in doubles each, with its transpose-reductions). B^T lam itself is kept (v_ctdz) for kkt_residual.
+  if (!c.box) {
+    axpy_pass2(c, c.Am, ne, c.Cm, n, c.slot_cons, 0, ns, os, n, v_t2, b1, -1.0, v_ctdz);
+    apply_Pinv(c, v_t2, ox);
+    return;
+  }
+#endif
   // lam scattered to constraint order (zero on inactive rows), then t2 = b1 - B^T lam.
   // B^T lam itself is kept (v_ctdz): kkt_residual needs exactly this product for the x block.
   _Pragma("unroll 1") for (int id = threadIdx.x; id < c.ldb; id += NT) {
