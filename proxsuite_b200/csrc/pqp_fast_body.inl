@@ -2060,7 +2060,8 @@ __device__ __noinline__ void tsym_sweep_invert(const Ctx& c, double* __restrict_
 #define PQP_TSYM_RANK1 tsym_rank1
 #endif
 #ifndef PQP_BTLAM_AXPY
-#define PQP_BTLAM_AXPY 0 // tile kernel: B^T lam of solve_kkt as an AXPY pass over the active rows of A_s / C_s (A/B switch)
+#define PQP_BTLAM_AXPY 0 // tile kernel: B^T lam of solve_kkt as an AXPY pass over the active rows of A_s / C_s. Measured (profiles/r02_ab_btlam_axpy.log):
+                         // 25.07 -> 26.84 ms (-7 %): A_s / C_s join the L2 working set (+120 KB per CTA) and the extra call costs 90 bytes of spills
 #endif
 #ifndef PQP_TILE_BLOCK
 #define PQP_TILE_BLOCK 0 // tile kernel: block (rank-4) insertion / deletion as in the big variant (A/B switch)
@@ -2228,7 +2229,7 @@ __device__ __noinline__ void solve_kkt(Ctx& c, const double* b1, const double* b
   // inequality slot s, weighted by lam[s] (one pass over ~n_s rows of n doubles instead of the dot form over all n rows of
   // Bt, n_eq + n_in doubles each, with its transpose-reductions). B^T lam itself is kept (v_ctdz) for kkt_residual.
   if (!c.box) {
-    axpy_pass2(c, c.Am, ne, c.Cm, n, c.slot_cons, 0, ns, os, n, v_t2, b1, -1.0, v_ctdz);
+    axpy_pass2(c, c.As, ne, c.Cs, n, c.slot_cons, 0, ns, os, n, v_t2, b1, -1.0, v_ctdz); // (the SCALED rows: c.Am / c.Cm are the model)
     apply_Pinv(c, v_t2, ox);
     return;
   }
