@@ -124,3 +124,28 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         proxqp.dense.QP(3, 0, 3)
+
+
+def test_free_solve_binds_both_overloads_like_the_reference(monkeypatch):
+    """expose-solve.hpp:54-79 / 115-142: (H, g, A, b, C, l, u, x, y, z, eps_abs, ...) and the box overload
+    (H, g, A, b, C, l, u, l_box, u_box, x, y, z, eps_abs, ...). The plain overload is tried first and rejected when the
+    argument at its eps_abs position is an array (host logic only: the solver behind it is stubbed)."""
+    from proxsuite_b200.proxqp import dense
+
+    seen = {}
+    monkeypatch.setattr(dense, "_solve", lambda **kw: seen.update(kw) or "results")
+    H, g, A, b, C, l, u = (np.eye(3), np.zeros(3), np.ones((1, 3)), np.ones(1), np.eye(3), -np.ones(3), np.ones(3))
+    x, y, z = np.zeros(3), np.zeros(1), np.zeros(3)
+    assert dense.solve(H, g, A, b, C, l, u, x, y, z, 1e-9, 0) == "results"
+    assert seen["x"] is x and seen["y"] is y and seen["z"] is z and seen["eps_abs"] == 1e-9 and seen["eps_rel"] == 0 and "l_box" not in seen
+    seen.clear()
+    lb, ub, zb = -2 * np.ones(3), 2 * np.ones(3), np.zeros(6)
+    dense.solve(H, g, A, b, C, l, u, lb, ub, x, y, zb, 1e-9, 0)  # index 10 is y: an array, so the box overload binds
+    assert seen["l_box"] is lb and seen["u_box"] is ub and seen["x"] is x and seen["y"] is y and seen["z"] is zb and seen["eps_abs"] == 1e-9
+    seen.clear()
+    dense.solve(H, g, A, b, C, l, u, l_box=lb, u_box=ub, eps_abs=1e-7)
+    assert seen["l_box"] is lb and seen["eps_abs"] == 1e-7 and "x" not in seen
+    with pytest.raises(TypeError):
+        dense.solve(H, g, A, b, C, l, u, x, y, z, 1e-9, eps_abs=1e-9)  # twice
+    with pytest.raises(TypeError):
+        dense.solve(H, g, nonsense=1)
