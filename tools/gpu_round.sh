@@ -17,6 +17,11 @@ PQP_LAYOUT=big timeout 400 compute-sanitizer --tool memcheck python tools/saniti
 timeout 400 compute-sanitizer --tool synccheck python tools/sanitize_target.py 2>&1 | tail -1 | tee gpurun_out/synccheck.log
 echo "== BASELINE shapes (cfg 2b / 3 / 4 / 5 at their own batch sizes)"; SWEEP_FULL=1 timeout 600 python tools/cfg_sweep.py 2b 3 4 5 2>&1 | tee gpurun_out/cfg_sweep_final.log
 if [ "${NCU_FULL:-1}" = "1" ]; then
+  # (the cfg-4 report is exported to CSV on the box and dropped: gpurun_out/ is capped at 64 MiB)
   echo "== ncu --set full (big variant, cfg 4 shape, 296 QPs)"; PQP_E2E=plain timeout 900 ncu --set full --clock-control none -k regex:pqp_solve_kernel -c 1 -f -o gpurun_out/solve_big_cfg4 python tools/ncu_target.py 296 1 cfg4 2>&1 | tail -2
-  echo "== ncu --set full (plain solve kernel)"; PQP_E2E=plain timeout 900 ncu --set full --clock-control none --import-source on -k regex:pqp_solve_kernel -c 1 -f -o gpurun_out/solve_full python tools/ncu_target.py 4096 1 2>&1 | tail -2
+  ncu -i gpurun_out/solve_big_cfg4.ncu-rep --page raw --csv > gpurun_out/solve_big_cfg4_raw.csv 2>/dev/null; rm -f gpurun_out/solve_big_cfg4.ncu-rep
+  echo "== ncu --set full (plain solve kernel, the bench launch)"; PQP_E2E=plain timeout 900 ncu --set full --clock-control none --import-source on -k regex:pqp_solve_kernel -c 1 -f -o gpurun_out/solve_full python tools/ncu_target.py 4096 1 2>&1 | tail -2
+  ncu -i gpurun_out/solve_full.ncu-rep --page raw --csv > gpurun_out/solve_full_raw.csv 2>/dev/null
+  # back in the container:  python tools/ncu_metrics_json.py gpurun_out/solve_full_raw.csv 4096 "<capture>"   (profiles/ncu_*.json, read by bench.py)
+  #                         python tools/ncu_funcs.py gpurun_out/solve_full.ncu-rep proxsuite_b200/libpqp_b200.so --kernel tilek   (per-function attribution)
 fi
